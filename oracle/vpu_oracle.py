@@ -1,0 +1,483 @@
+"""CPU oracle: a plain restatement of the reference per-click VPUFormer forward.
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product (pvpuformer_b200/) never does.
+
+Why a restatement exists although the reference is importable Python: /root/reference does not
+travel to the GPU box, so GPU parity tests need a checker that does.  Every function cites the
+reference file:line it follows.  The restatement is PINNED against the unmodified reference run
+in the build container (tests/test_oracle_vs_reference.py, and tests/golden/*.npz produced by
+oracle/make_golden.py); the reference itself ships no tests or golden vectors,
+so that pin -- outputs of the reference run here -- is the anchor of all parity claims.
+
+Arithmetic: torch CPU fp32 (+ numpy float64 where the reference uses it), no fused/fast paths.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+try:  # only needed for prompt types 1/2 (box / scribble rasterisation)
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+
+# --------------------------------------------------------------------------------------------
+# A3  disk maps  (reference isegm/model/ops.py:347-382, use_disks=True, spatial_scale=1)
+# --------------------------------------------------------------------------------------------
+def disk_maps(points, rows, cols, norm_radius=5):
+    """points [B,2n,3] (row, col, order) any float/int dtype -> float32 [B,2,rows,cols] in {0,1}."""
+    B = points.shape[0]
+    n = points.shape[1] // 2
+    pts = points.reshape(-1, points.shape[2])
+    xy = pts[:, :2]
+    invalid = xy.max(dim=1)[0] < 0                                  # ops.py:352
+    rr = torch.arange(rows, dtype=torch.float32).view(1, rows, 1)
+    cc = torch.arange(cols, dtype=torch.float32).view(1, 1, cols)
+    # ops.py:356-365: coords.add_(-points) is an in-place add on a float32 grid: the difference is
+    # formed in the promoted dtype (float64 for float64 clicks) and rounded to float32 once;
+    # then squared and summed in float32.
+    if xy.dtype == torch.float64:
+        dr = (rr.double() - xy[:, 0].view(-1, 1, 1)).float()
+        dc = (cc.double() - xy[:, 1].view(-1, 1, 1)).float()
+    else:
+        dr = rr - xy[:, 0].to(torch.float32).view(-1, 1, 1)
+        dc = cc - xy[:, 1].to(torch.float32).view(-1, 1, 1)
+    d = dr * dr + dc * dc
+    d[invalid] = 1e6                                                # ops.py:368
+    d = d.view(B * 2, n, rows, cols).min(dim=1)[0].view(B, 2, rows, cols)   # ops.py:370-372
+    return (d <= float(norm_radius) ** 2).float()                   # ops.py:375
+
+
+# --------------------------------------------------------------------------------------------
+# A2  box / scribble raster into the coord features (reference isegm/model/is_model.py:78-146)
+# --------------------------------------------------------------------------------------------
+def raster_box(plane_u8, box):
+    """cv2.rectangle thickness 3 on a {0,255} uint8 plane (is_model.py:107-109)."""
+    xc, yc, w, h = int(box[0]), int(box[1]), int(box[2]), int(box[3])
+    x0, x1, y0, y1 = xc - w // 2, xc + w // 2, yc - h // 2, yc + h // 2
+    cv2.rectangle(plane_u8, (x0, y0), (x1, y1), (255, 255, 255), 3)
+    return plane_u8
+
+
+def raster_scribble(plane_u8, scribble):
+    """cv2.polylines thickness 3, open curve (is_model.py:128-129). scribble [S,2] (col,row)."""
+    curve = np.column_stack((scribble[:, 0].astype(np.int32), scribble[:, 1].astype(np.int32)))
+    return cv2.polylines(plane_u8, [curve], False, (255, 255, 255), 3)
+
+
+def coord_features(image4, points, prompts=None, as_prompt_type=0, norm_radius=5):
+    """is_model.py:78-95: disks, optional box/scribble OR-in, cat(prev_mask, disks) -> [B,3,H,W]."""
+    B, _, H, W = image4.shape
+    prev = image4[:, 3:, :, :]
+    cf = disk_maps(points, H, W, norm_radius)
+    n = points.shape[1] // 2
+    if as_prompt_type != 0:
+        _, boxes, (scribbles, rects) = prompts
+        for b in range(B):
+            if as_prompt_type == 1:
+                bx = boxes[b].cpu().numpy()
+                ch = 0 if bx[4] < n else 1                            # is_model.py:101-104
+                plane = np.uint8(cf[b, ch].numpy().astype(int) * 255)
+                plane = raster_box(plane, bx)
+                cf[b, ch] = torch.from_numpy(plane // 255).float()
+            elif as_prompt_type == 2:
+                plane = np.uint8(cf[b, 0].numpy().astype(int) * 255)
+                plane = raster_scribble(plane, scribbles[b][0])
+                cf[b, 0] = torch.from_numpy(plane // 255).float()
+    return torch.cat((prev, cf), dim=1)
+
+
+# --------------------------------------------------------------------------------------------
+# A4-A6  PPuE: Gaussian mapping of clicks / boxes / scribbles to the unified 899-d prompt rows
+# --------------------------------------------------------------------------------------------
+def click_table(sigma=3):
+    """ops.py:51-61: 19-tap float32 Gaussian with the centre raised by 1 (heighten_peak)."""
+    r = int(sigma * 3)
+    k = np.arange(0, 2 * r + 1, 1, np.float32)
+    t = np.exp(-((k - (2 * r + 1) // 2) ** 2) / (2 * sigma ** 2))
+    t[(2 * r + 1) // 2] += 1
+    return t, r
+
+
+def _window_write(vec, p, radius, table, size):
+    """ops.py:96-103 for one axis: copy table into vec[p-radius : p+radius+1], clipped."""
+    ul, br = int(p - radius), int(p + radius + 1)
+    g0, g1 = max(0, -ul), min(size, br) - ul
+    i0, i1 = max(0, ul), min(size, br)
+    if i1 > i0 and g1 > g0:
+        vec[i0:i1] = table[g0:g1]
+
+
+def _in_img(x, y, w, h):
+    return not ((x < 0) or (x > w) or (y < 0) or (y > h))             # ops.py:63-67 ('>' not '>=')
+
+
+def ppue_click_row(pt, size=448, sigma=3):
+    """ops.py:80-104 for one point -> (vec_x[size], vec_y[size]) float64."""
+    table, r = click_table(sigma)
+    p = np.asarray(pt, dtype=np.float64)[:2]
+    p = (p * 4 / 4).astype('int32')                                  # trunc toward zero
+    x, y = int(p[0]), int(p[1])
+    vx, vy = np.zeros(size), np.zeros(size)
+    ul, br = (x - r, y - r), (x + r + 1, y + r + 1)
+    if (not _in_img(ul[0], ul[1], size, size)) and (not _in_img(br[0], br[1], size, size)):
+        return vx, vy                                                # ops.py:90-94 (drop)
+    _window_write(vx, x, r, table, size)
+    _window_write(vy, y, r, table, size)
+    return vx, vy
+
+
+def ppue_box_row(center, wh, size=448):
+    """ops.py:138-202 for one box: (x_c, y_c), (W, H) -> (vec_x, vec_y) float64."""
+    vx, vy = np.zeros(size), np.zeros(size)
+    center = np.asarray(center)
+    wh = np.asarray(wh)
+    if np.sum(center) + np.sum(wh) == 0:
+        return vx, vy
+    tabs, rads = [], []
+    for d in (wh[0], wh[1]):
+        d = np.int32(d)
+        ks = d // 2 * 2 - 1
+        rad = (ks - 1) // 2
+        sig = rad // 3
+        if sig == 0:
+            return np.zeros(size), np.zeros(size)
+        c = ks // 2
+        k = np.arange(0, ks, 1, np.float32)
+        # float32 array / numpy int32 scalar -> float64 under numpy>=2 (the oracle's numpy)
+        tabs.append(np.exp(-((k - c) ** 2) / (2 * sig ** 2)))
+        rads.append(int(rad))
+    p = (center * 4 / 4).astype('int32')
+    x, y = int(p[0]), int(p[1])
+    ul = (x - rads[0], y - rads[1])
+    br = (x + rads[0] + 1, y + rads[1] + 1)
+    if (not _in_img(ul[0], ul[1], size, size)) and (not _in_img(br[0], br[1], size, size)):
+        return vx, vy
+    _window_write(vx, x, rads[0], tabs[0], size)
+    _window_write(vy, y, rads[1], tabs[1], size)
+    return vx, vy
+
+
+def scribble_select(scribble, rect, size=448, rng=random):
+    """Host half of ops.py:245-295: the data-dependent, `random`-driven choice of one scribble
+    sample per column / per row.  Returns two int32 arrays sel_x[size], sel_y[size] holding the
+    OFFSET (coordinate minus box origin) whose Gaussian is written at that position, or INT_MIN
+    where nothing is written.  Consumes `rng.randint` in exactly the reference's order."""
+    NONE = np.iinfo(np.int32).min
+    sel_x = np.full(size, NONE, np.int32)
+    sel_y = np.full(size, NONE, np.int32)
+    scribble = np.asarray(scribble).astype(np.int32)
+    rect = np.asarray(rect)
+    if np.sum(scribble) + np.sum(rect) == 0:
+        return sel_x, sel_y
+    scribble = (scribble * 4 / 4).astype('int32')
+    x0, y0, w0, h0 = [int(v) for v in rect]
+    x0, y0, w0, h0 = min(x0, size), min(y0, size), min(w0, size), min(h0, size)
+    w_box = x0 - w0 // 2
+    h_box = y0 - h0 // 2
+    for xi in range(w0):
+        idx = np.argwhere(scribble[:, 0] == xi)
+        if len(idx) != 0:
+            j = rng.randint(0, len(idx) - 1)
+            pt = scribble[j]                                         # ops.py:274-275 (index quirk)
+            xs, hs = int(pt[0]), int(pt[1])
+            sel_x[xi] = hs - h_box
+            drop = np.argwhere((scribble[:, 0] == xs) & (scribble[:, 1] == hs))
+            scribble = np.delete(scribble, drop, axis=0)
+    for yj in range(h0):
+        idx = np.argwhere(scribble[:, 1] == yj)
+        if len(idx) != 0:
+            j = rng.randint(0, len(idx) - 1)
+            pt = scribble[j]
+            sel_y[yj] = int(pt[0]) - w_box
+    return sel_x, sel_y
+
+
+def ppue_scribble_row(scribble, rect, size=448, sigma=3, rng=random):
+    """ops.py:245-325 -> (vec_x, vec_y) float64: exp(-(offset)^2 / 18) at the selected slots."""
+    sel_x, sel_y = scribble_select(scribble, rect, size, rng)
+    NONE = np.iinfo(np.int32).min
+    vx, vy = np.zeros(size), np.zeros(size)
+    for v, s in ((vx, sel_x), (vy, sel_y)):
+        m = s != NONE
+        # np.int32 scalar ** 2 / python int -> float64
+        v[m] = np.exp(-(s[m].astype(np.int64) ** 2) / (2 * sigma ** 2))
+    return vx, vy
+
+
+def ppue(points, prompts=None, as_prompt_type=0, size=448, num_max_points=24, rng=random):
+    """is_vpu_model.py:189-352 -> float64 [B, 2*num_max_points, 2*size+3]."""
+    pts = points.detach().cpu()
+    B, N2, _ = pts.shape
+    n = N2 // 2
+    D = 2 * size + 3
+    xy = pts[:, :, :2].numpy()
+    labels = pts[:, :, 2]
+    out = np.zeros((B, N2, D))
+    for b in range(B):
+        for i in range(N2):
+            vx, vy = ppue_click_row(xy[b, i], size)
+            out[b, i, :size] = vx
+            out[b, i, size:2 * size] = vy
+            out[b, i, 2 * size + (0 if i < n else 1)] = 1.0
+    out = torch.from_numpy(out)
+    nap = torch.zeros(D, dtype=torch.float64)
+    nap[-1] = 1
+    out[labels == -1] = nap                                          # is_vpu_model.py:215-216
+    if as_prompt_type == 1:
+        boxes = prompts[1].cpu().numpy()
+        for b in range(B):
+            vx, vy = ppue_box_row(boxes[b, :2], boxes[b, 2:4], size)
+            row = torch.zeros(D, dtype=torch.float64)
+            row[:size] = torch.from_numpy(vx)
+            row[size:2 * size] = torch.from_numpy(vy)
+            row[2 * size + (0 if boxes[b, 4] < n else 1)] = 1.0      # is_vpu_model.py:270-272
+            out[b, int(boxes[b, 4])] = row                           # is_vpu_model.py:276-277
+    elif as_prompt_type == 2:
+        scribbles, rects = prompts[2]
+        scribbles = np.asarray(scribbles).astype(np.int32)
+        for b in range(B):
+            vx, vy = ppue_scribble_row(scribbles[b][0], rects[b][0], size, rng=rng)
+            valid = torch.nonzero(labels[b, :n] != -1)               # is_vpu_model.py:329,336-338
+            if len(valid) > 0:
+                row = torch.zeros(D, dtype=torch.float64)
+                row[:size] = torch.from_numpy(vx)
+                row[size:2 * size] = torch.from_numpy(vy)
+                row[2 * size] = 1.0
+                out[b, int(valid[-1, 0])] = row
+    if n != num_max_points:                                          # is_vpu_model.py:218-228
+        pad = nap.view(1, 1, -1).repeat(B, num_max_points - n, 1)
+        out = torch.cat([out[:, :n], pad, out[:, n:], pad], dim=1)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Model blocks
+# --------------------------------------------------------------------------------------------
+def _lin(sd, key, x):
+    return F.linear(x, sd[key + ".weight"], sd[key + ".bias"])
+
+
+def _ln(sd, key, x, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[key + ".weight"], sd[key + ".bias"], eps)
+
+
+def vit_attention(sd, pre, x, heads):
+    """models_vit.py:43-56."""
+    B, N, C = x.shape
+    qkv = _lin(sd, pre + ".qkv", x).reshape(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = ((q @ k.transpose(-2, -1)) * ((C // heads) ** -0.5)).softmax(dim=-1)
+    return _lin(sd, pre + ".proj", (attn @ v).transpose(1, 2).reshape(B, N, C))
+
+
+def vit_block(sd, pre, x, heads):
+    """models_vit.py:72-75 with LayerNorm eps 1e-6 (models_vit.py:126)."""
+    x = x + vit_attention(sd, pre + ".attn", _ln(sd, pre + ".norm1", x, 1e-6), heads)
+    h = F.gelu(_lin(sd, pre + ".mlp.fc1", _ln(sd, pre + ".norm2", x, 1e-6)))
+    return x + _lin(sd, pre + ".mlp.fc2", h)
+
+
+def window_partition(x, grid, win):
+    """models_vit.py:225-239: [B,N,C] -> [B*nw*nw, win*win, C]."""
+    B, N, C = x.shape
+    nw = grid // win
+    x = x.view(B, nw, win, nw, win, C).permute(0, 1, 3, 2, 4, 5).contiguous()
+    return x.view(B * nw * nw, win * win, C)
+
+
+def window_merge(x, grid, win):
+    """models_vit.py:242-255."""
+    Bw, _, C = x.shape
+    nw = grid // win
+    B = Bw // (nw * nw)
+    x = x.view(B, nw, nw, win, win, C).permute(0, 1, 3, 2, 4, 5).contiguous()
+    return x.view(B, grid * grid, C)
+
+
+def vit_backbone(sd, cfg, image_norm, coord_feats, taps=None):
+    """is_vpu_model.py:385-386 + models_vit.py:257-287."""
+    p = cfg.patch
+    x = F.conv2d(image_norm, sd["backbone.patch_embed.proj.weight"], sd["backbone.patch_embed.proj.bias"],
+                 stride=p).flatten(2).transpose(1, 2)
+    c = F.conv2d(coord_feats, sd["patch_embed_coords.proj.weight"], sd["patch_embed_coords.proj.bias"],
+                 stride=p).flatten(2).transpose(1, 2)
+    x = x + c
+    x = x + sd["backbone.pos_embed"][:, 1:]
+    if taps is not None:
+        taps["tokens_embed"] = x
+    group = cfg.blocks_per_group
+    patchified = False
+    for i in range(1, cfg.depth + 1):
+        if i % group:
+            if not patchified:
+                x = window_partition(x, cfg.grid, cfg.window_grid)
+                patchified = True
+        else:
+            x = window_merge(x, cfg.grid, cfg.window_grid)
+            patchified = False
+        x = vit_block(sd, "backbone.blocks.%d" % (i - 1), x, cfg.num_heads)
+        if taps is not None and i in (1, group, cfg.depth):
+            taps["tokens_block%d" % i] = window_merge(x, cfg.grid, cfg.window_grid) if patchified else x
+    return x
+
+
+def dma_attention(sd, pre, q, k, v, heads):
+    """transformer.py:499-521."""
+    q, k, v = _lin(sd, pre + ".q_proj", q), _lin(sd, pre + ".k_proj", k), _lin(sd, pre + ".v_proj", v)
+
+    def split(t):
+        b, n, c = t.shape
+        return t.reshape(b, n, heads, c // heads).transpose(1, 2)
+    q, k, v = split(q), split(k), split(v)
+    d = q.shape[-1]
+    attn = torch.softmax((q @ k.permute(0, 1, 3, 2)) / math.sqrt(d), dim=-1)
+    o = (attn @ v).transpose(1, 2)
+    return _lin(sd, pre + ".out_proj", o.reshape(o.shape[0], o.shape[1], -1))
+
+
+def pos2d(d_model, height, width):
+    """transformer.py:290-318 -> [1, H*W, d_model]."""
+    pe = torch.zeros(d_model, height, width)
+    d = d_model // 2
+    div = torch.exp(torch.arange(0., d, 2) * -(math.log(10000.0) / d))
+    pw = torch.arange(0., width).unsqueeze(1)
+    ph = torch.arange(0., height).unsqueeze(1)
+    pe[0:d:2] = torch.sin(pw * div).transpose(0, 1).unsqueeze(1).repeat(1, height, 1)
+    pe[1:d:2] = torch.cos(pw * div).transpose(0, 1).unsqueeze(1).repeat(1, height, 1)
+    pe[d::2] = torch.sin(ph * div).transpose(0, 1).unsqueeze(2).repeat(1, 1, width)
+    pe[d + 1::2] = torch.cos(ph * div).transpose(0, 1).unsqueeze(2).repeat(1, 1, width)
+    return pe.reshape(-1, 1, height * width).permute(1, 2, 0)
+
+
+def dma(sd, cfg, q0, x, taps=None):
+    """transformer.py:323-384 + 432-463 (TwoWayTransformer, return_intermediate=True)."""
+    H = cfg.dma_heads
+    key_pe = pos2d(cfg.embed_dim, cfg.grid, cfg.grid)
+    queries, keys = q0, x
+    inter = []
+    for j in range(cfg.dma_depth):
+        l = "neck.att.layers.%d" % j
+        if j == 0:                                                    # skip_first_layer_pe
+            queries = dma_attention(sd, l + ".self_attn", queries, queries, queries, H)
+        else:
+            q = queries + q0
+            queries = queries + dma_attention(sd, l + ".self_attn", q, q, queries, H)
+        queries = _ln(sd, l + ".norm1", queries, 1e-5)
+        q, k = queries + q0, keys + key_pe
+        queries = _ln(sd, l + ".norm2",
+                      queries + dma_attention(sd, l + ".cross_attn_token_to_image", q, k, keys, H), 1e-5)
+        m = _lin(sd, l + ".mlp.lin2", F.relu(_lin(sd, l + ".mlp.lin1", queries)))
+        queries = _ln(sd, l + ".norm3", queries + m, 1e-5)
+        q, k = queries + q0, keys + key_pe
+        keys = _ln(sd, l + ".norm4",
+                   keys + dma_attention(sd, l + ".cross_attn_image_to_token", k, q, queries, H), 1e-5)
+        if j != cfg.dma_depth - 1:
+            inter.append((queries, keys))
+    q, k = queries + q0, keys + key_pe
+    queries = _ln(sd, "neck.att.norm_final_attn",
+                  queries + dma_attention(sd, "neck.att.final_attn_token_to_image", q, k, keys, H), 1e-5)
+    inter.append((queries, keys))
+    return inter
+
+
+def _gn(sd, key, x):
+    return F.group_norm(x, 1, sd[key + ".weight"], sd[key + ".bias"], 1e-5)
+
+
+def neck(sd, cfg, x, ppue_rows, taps=None):
+    """is_vpu_model.py:93-136 (SimpleFPN.forward, edloss=True)."""
+    B, N, C = x.shape
+    q = _lin(sd, "neck.ffn_layer.lin2", F.relu(_lin(sd, "neck.ffn_layer.lin1", ppue_rows.type_as(x))))
+    if taps is not None:
+        taps["q_ffn"] = q
+    (q2, k2), (q3, k3), (q4, k4) = dma(sd, cfg, q, x, taps)
+    q_out = q + q2 + q3 + q4
+    if taps is not None:
+        taps["q_out"] = q_out
+        taps["dma_q_final"] = q4
+        taps["dma_k_final"] = k4
+    xs = []
+    for ql, kl in ((q2, k2), (q3, k3), (q4, k4)):
+        cg = ql.max(dim=1).values.sigmoid().unsqueeze(1)
+        sg = kl.max(dim=2).values.sigmoid().unsqueeze(2)
+        xs.append(x + x * cg + x * sg)
+    g = cfg.grid
+
+    def to_map(t):
+        return t.transpose(-1, -2).reshape(B, C, g, g)
+    x0, x2, x3, x4 = to_map(x), to_map(xs[0]), to_map(xs[1]), to_map(xs[2])
+
+    t = F.conv_transpose2d(x0, sd["neck.down_4.0.weight"], sd["neck.down_4.0.bias"], stride=2)
+    t = F.gelu(_gn(sd, "neck.down_4.1", t))
+    t = F.conv_transpose2d(t, sd["neck.down_4.3.weight"], sd["neck.down_4.3.bias"], stride=2)
+    t = _gn(sd, "neck.down_4.4", t)
+    t = F.conv2d(t, sd["neck.down_4.5.weight"], sd["neck.down_4.5.bias"])
+    d4 = F.gelu(_gn(sd, "neck.down_4.6", t))
+
+    t = F.conv_transpose2d(x2, sd["neck.down_8.0.weight"], sd["neck.down_8.0.bias"], stride=2)
+    t = _gn(sd, "neck.down_8.1", t)
+    t = F.conv2d(t, sd["neck.down_8.2.weight"], sd["neck.down_8.2.bias"])
+    d8 = F.gelu(_gn(sd, "neck.down_8.3", t))
+
+    t = F.conv2d(x3, sd["neck.down_16.0.weight"], sd["neck.down_16.0.bias"])
+    d16 = F.gelu(_gn(sd, "neck.down_16.1", t))
+
+    t = F.conv2d(x4, sd["neck.down_32.0.weight"], sd["neck.down_32.0.bias"], stride=2)
+    t = _gn(sd, "neck.down_32.1", t)
+    t = F.conv2d(t, sd["neck.down_32.2.weight"], sd["neck.down_32.2.bias"])
+    d32 = F.gelu(_gn(sd, "neck.down_32.3", t))
+    if taps is not None:
+        taps["pyr4"], taps["pyr8"], taps["pyr16"], taps["pyr32"] = d4, d8, d16, d32
+    return [d4, d8, d16, d32], q_out
+
+
+def head(sd, cfg, feats, q_out, taps=None):
+    """swin_transformer.py:723-767 (forward_feat), eval mode (Dropout2d inactive)."""
+    size = feats[0].shape[2:]
+    outs = []
+    for i, f in enumerate(feats):
+        c = F.relu(F.conv2d(f, sd["head.convs.%d.conv.weight" % i], sd["head.convs.%d.conv.bias" % i]))
+        outs.append(F.interpolate(c, size=size, mode="bilinear", align_corners=False))
+    out = F.relu(F.conv2d(torch.cat(outs, dim=1), sd["head.fusion_conv.conv.weight"],
+                          sd["head.fusion_conv.conv.bias"]))
+    query = _lin(sd, "head.ffn_layer.lin2", F.relu(_lin(sd, "head.ffn_layer.lin1", q_out)))
+    flat = out.flatten(2)
+    seg = F.conv2d(out, sd["head.conv_seg.weight"], sd["head.conv_seg.bias"])
+    logits = (torch.matmul(F.normalize(query, p=2, dim=2), F.normalize(flat, p=2, dim=1)) + 1) / 2
+    B, n, HW = logits.shape
+    s = int(math.sqrt(HW))
+    if taps is not None:
+        taps["head_feat"] = out
+    return seg, logits.view(B, n, s, s)
+
+
+def forward(sd, cfg, image4, points, prompts=None, as_prompt_type=0, taps=None, rng=random,
+            want_aux=True):
+    """is_vpu_model.py:422-438.  image4 [B,4,H,W] fp32, points [B,2n,3]."""
+    mean = torch.tensor(cfg.norm_mean, dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.tensor(cfg.norm_std, dtype=torch.float32).view(1, 3, 1, 1)
+    img = (image4[:, :3].clone() - mean) / std                       # ops.py:403-407
+    cf = coord_features(image4, points, prompts, as_prompt_type, cfg.norm_radius)
+    if taps is not None:
+        taps["coord_features"] = cf
+    x = vit_backbone(sd, cfg, img, cf, taps)
+    if taps is not None:
+        taps["backbone_features"] = x
+    pv_points = prompts[0] if as_prompt_type != 0 else points         # is_vpu_model.py:396-397
+    rows = ppue(pv_points, prompts, as_prompt_type, cfg.img_size, cfg.num_max_points, rng)
+    if taps is not None:
+        taps["ppue"] = rows
+    feats, q_out = neck(sd, cfg, x, rows, taps)
+    seg, logits = head(sd, cfg, feats, q_out, taps)
+    if taps is not None:
+        taps["seg_lowres"], taps["aux_lowres"] = seg, logits
+    H, W = image4.shape[2:]
+    out = {"instances": F.interpolate(seg, size=(H, W), mode="bilinear", align_corners=True)}
+    out["instances_aux"] = F.interpolate(logits, size=(H, W), mode="bilinear", align_corners=True) \
+        if want_aux else None
+    return out
