@@ -1,0 +1,114 @@
+/* vpuformer_b200 -- C ABI of the B200-native per-click VPUFormer forward.
+ *
+ * The reference (XuZhang1211/PVPUFormer) has no FFI: its boundary for this path is the Python
+ * call  net(image, points, prompts, as_prompt_type) -> {'instances', 'instances_aux'}
+ * (reference isegm/model/is_vpu_model.py:422-438, called from
+ * isegm/inference/predictors/base.py:104,163,177).  This header is what a binding of that call
+ * targets; pvpuformer_b200/model.py is the ctypes binding.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error with a thread-local
+ * message in vpu_last_error().  No exceptions cross the ABI.  All data pointers are DEVICE
+ * pointers owned by the caller (torch tensors kept alive by the caller) unless marked host.
+ * Nothing allocates, synchronises or uses the default stream inside vpu_forward: all work is
+ * enqueued on `stream` (a cudaStream_t passed as void*).  One handle per (device, thread).
+ * There is no CPU or library fallback: on a non-sm_100 device every compute entry fails.
+ */
+#ifndef VPUFORMER_B200_H
+#define VPUFORMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vpu_context* vpu_handle;
+
+/* Model geometry: reference models_vit.py:306-319 (ViT-B/L/H factories),
+ * models/iSegNet/vpu_base448_cocolvis.py:11-56, is_vpu_model.py:19-86 (neck), swin_transformer.py:666-721 (head). */
+typedef struct vpu_dims {
+    int32_t img_size;        /* 448 */
+    int32_t patch;           /* 16 (B/L) or 14 (H) */
+    int32_t embed_dim;       /* 768 / 1024 / 1280 */
+    int32_t depth;           /* 12 / 24 / 32 */
+    int32_t num_heads;       /* 12 / 16 / 16 */
+    int32_t num_max_points;  /* 24 -> 48 prompt queries */
+    int32_t dma_depth;       /* 3 */
+    int32_t dma_heads;       /* 8 */
+    int32_t dma_mlp_dim;     /* 1024 */
+    int32_t ppue_ffn_dim;    /* 2048 */
+    int32_t head_channels;   /* 256 */
+    int32_t out_dims[4];     /* 128, 256, 512, 1024 */
+    float norm_radius;       /* 5 (click disk radius, is_model.py:10, ops.py:375) */
+} vpu_dims;
+
+enum { VPU_F32 = 0, VPU_BF16 = 1, VPU_I32 = 2, VPU_F64 = 3, VPU_U8 = 4 };
+
+const char* vpu_last_error(void);
+int vpu_version(void);
+
+/* ---- lifecycle (replaces VitMultiGaussianVector_ed_Model.__init__ / load_state_dict,
+ *      reference is_vpu_model.py:142-186, inference/utils.py:21-46) ---- */
+int vpu_create(vpu_handle* out, const vpu_dims* dims);
+void vpu_destroy(vpu_handle h);
+/* Bind one packed weight tensor (device memory, kept alive by the caller).  Keys and layouts are
+ * listed in DESIGN.md ("packed weights"); pvpuformer_b200/packing.py produces them from a
+ * reference state_dict. */
+int vpu_bind_weight(vpu_handle h, const char* key, const void* dev_ptr, int dtype, const int64_t* shape, int rank);
+int vpu_set_scalar(vpu_handle h, const char* key, float value);
+/* Optional: HOST pointer to the PPuE click Gaussian taps (reference ops.py:51-61 computes them with
+ * numpy float32; passing numpy's values makes the click rows bit-identical).  Default: same formula in C. */
+int vpu_set_click_table(vpu_handle h, const float* host_table, int taps);
+/* Check that every weight the forward needs is bound with the right dtype/shape. */
+int vpu_finalize(vpu_handle h);
+
+/* ---- the hot path (replaces forward(), reference is_vpu_model.py:422-438) ---- */
+size_t vpu_workspace_bytes(vpu_handle h, int B);
+/* Offset/size of a named intermediate inside the workspace (parity taps). */
+int vpu_workspace_lookup(vpu_handle h, int B, const char* name, size_t* offset, size_t* bytes);
+
+typedef struct vpu_prompts {
+    const double* points;        /* [B, 2n, 3] (row, col, order), -1 padded: disks AND (type 0) PPuE */
+    const double* ppue_points;   /* [B, 2n_ppue, 3] = prompts[0] for types 1/2 (is_vpu_model.py:396-397); NULL => points */
+    int32_t n;                   /* clicks per half in `points` (1..24) */
+    int32_t n_ppue;              /* clicks per half in `ppue_points` */
+    int32_t type;                /* as_prompt_type: 0 clicks, 1 box, 2 scribble */
+    const int32_t* boxes;        /* [B,5] (x_c, y_c, w, h, slot)                      type 1 */
+    const int32_t* scrib_sel;    /* [B,2,img] selected offsets or INT32_MIN           type 2 */
+    const int32_t* scrib_slot;   /* [B] PPuE row of the scribble or -1                type 2 */
+    const uint8_t* extra_mask;   /* [B,2,img,img] box/scribble raster OR-ed into the click disks; may be NULL */
+} vpu_prompts;
+
+int vpu_forward(vpu_handle h, const float* image4 /* [B,4,img,img] fp32 */, const vpu_prompts* prompts, int B,
+                float* instances /* [B,1,img,img] */, float* instances_aux /* [B,48,img,img] or NULL */,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stage entry points (also what the parity tests call) ---- */
+/* PPuE rows (reference is_vpu_model.py:189-352, ops.py:39-325) -> out [B, 2*num_max_points, 2*img+3] fp32 */
+int vpu_ppue(vpu_handle h, const vpu_prompts* prompts, int B, float* out, void* stream);
+/* cat(prev_mask, disks|raster) (reference is_model.py:78-95, ops.py:347-382) -> out [B,3,img,img] fp32 */
+int vpu_coord_features(vpu_handle h, const float* image4, const vpu_prompts* prompts, int B, float* out, void* stream);
+
+/* ---- kernel-level entry points (unit parity tests; all operands bf16/fp32 device pointers) ---- */
+/* out[M,N] = act(A[M,K] * W[N,K]^T + bias[N] + bias2d[m % rows, N] + residual[M,N]) */
+int vpu_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* bias,
+             const float* bias2d, int bias2d_rows, const void* residual, int residual_dtype, int ldr, int act /*0,1 gelu,2 relu*/,
+             void* out, int out_dtype, int ldo, int impl /*0 tcgen05, 1 mma.sync cross-check*/, void* stream);
+/* ConvTranspose2d(k=2,s=2) as GEMM + pixel-shuffle store: A [B*g*g, K] -> out NHWC [B, 2g, 2g, cout] bf16 */
+int vpu_gemm_pixel_shuffle(const void* A_bf16, const void* W_bf16, int M, int cout, int K, const float* bias4, int g,
+                           void* out_bf16, int impl, void* stream);
+/* softmax(q k^T * scale) v; window=0: contiguous sequences; window>0: 224-px window regrouping */
+int vpu_attention(const void* q, int ldq, int qoff, const void* k, int ldk, int koff, const void* v, int ldv, int voff,
+                  void* o, int ldo, int Sq, int Sk, int heads, int head_dim, int nprob, float scale, int window,
+                  int grid, void* stream);
+int vpu_layernorm(const float* in, const float* gamma, const float* beta, float eps, int rows, int C, float* out_f32,
+                  void* out_bf16, const float* pe, void* out_pe_bf16, float* rowmax, void* stream);
+int vpu_groupnorm_nhwc(void* x_bf16, int B, int64_t per_sample, int C, const float* gamma, const float* beta, int gelu,
+                       void* scratch /* >= B*8200 bytes */, void* stream);
+int vpu_upsample_align_corners(const float* in, float* out, int h, int w, int H, int W, int64_t planes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPUFORMER_B200_H */

@@ -1,0 +1,684 @@
+// C-ABI + host orchestration of the per-click forward (include/vpuformer_b200.h).
+// Stage order follows reference is_vpu_model.py:422-438 / 383-419; every stage enqueues
+// hand-written sm_100a kernels on the caller's stream.  No allocation, no sync, no fallback.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vpuformer_b200.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "prompt.cuh"
+
+namespace vpu {
+const char* last_error();
+
+struct Tensor {
+    const void* p = nullptr;
+    int dtype = 0;
+    std::vector<int64_t> shape;
+};
+
+struct Buf {
+    std::string name;
+    size_t off, bytes;
+};
+
+struct Plan {
+    std::vector<Buf> bufs;
+    size_t total = 0;
+    size_t add(const char* name, size_t bytes) {
+        total = (total + 1023) & ~size_t(1023);
+        bufs.push_back({name, total, bytes});
+        const size_t o = total;
+        total += bytes;
+        return o;
+    }
+    const Buf* find(const char* name) const {
+        for (auto& b : bufs)
+            if (b.name == name) return &b;
+        return nullptr;
+    }
+};
+
+}  // namespace vpu
+
+using namespace vpu;
+
+struct vpu_context {
+    vpu_dims d;
+    std::unordered_map<std::string, Tensor> w;
+    std::unordered_map<std::string, float> scalars;
+    bool finalized = false;
+    int gemm_impl = 0;
+    float click_table[32];
+    int click_radius = 9;
+
+    int C() const { return d.embed_dim; }
+    int grid() const { return d.img_size / d.patch; }
+    int N() const { return grid() * grid(); }
+    int Q() const { return 2 * d.num_max_points; }
+    int K0() const { return 6 * d.patch * d.patch; }
+    int ppue_dim() const { return 2 * d.img_size + 3; }
+    int ppue_ld() const { return (ppue_dim() + 7) / 8 * 8; }
+    int d4() const { return std::max(d.out_dims[0] * 2, d.embed_dim / 2); }
+    int d8() const { return std::max(d.out_dims[1], d.embed_dim / 2); }
+    int d32() const { return std::max(d.out_dims[3], d.embed_dim * 2); }
+    int group() const { return d.depth == 12 ? 6 : d.depth / 4; }
+};
+
+namespace {
+
+Plan make_plan(const vpu_context& h, int B) {
+    Plan p;
+    const size_t C = h.C(), N = h.N(), M = (size_t)B * N, Q = h.Q(), MQ = (size_t)B * Q, g = h.grid();
+    const size_t g2 = 2 * g, g4 = 4 * g, gh = g / 2, hc = h.d.head_channels;
+    p.add("ppue", (size_t)B * Q * h.ppue_dim() * 4);
+    p.add("ppue_b", MQ * h.ppue_ld() * 2);
+    p.add("A0", M * h.K0() * 2);
+    p.add("X", M * C * 4);
+    p.add("Xn", M * C * 2);
+    p.add("QKV", M * 3 * C * 2);
+    p.add("AO", M * C * 2);
+    p.add("H", M * 4 * C * 2);
+    // DMA
+    p.add("T1", MQ * h.d.ppue_ffn_dim * 2);
+    p.add("Q0", MQ * C * 4);
+    p.add("Q0b", MQ * C * 2);
+    p.add("Qt", MQ * C * 4);
+    p.add("Qb", MQ * C * 2);
+    p.add("QPb", MQ * C * 2);
+    p.add("ql0", MQ * C * 4);
+    p.add("ql1", MQ * C * 4);
+    p.add("ql2", MQ * C * 4);
+    p.add("qfin", MQ * C * 4);
+    p.add("SQK", MQ * 2 * C * 2);
+    p.add("SV", MQ * C * 2);
+    p.add("SO", MQ * C * 2);
+    p.add("T", MQ * C * 4);
+    p.add("TQ", MQ * (C / 2) * 2);
+    p.add("TO", MQ * (C / 2) * 2);
+    p.add("MH", MQ * h.d.dma_mlp_dim * 2);
+    p.add("IK", MQ * (C / 2) * 2);
+    p.add("IV", MQ * (C / 2) * 2);
+    p.add("X0b", M * C * 2);
+    p.add("Kb", M * C * 2);
+    p.add("KVQ", M * (3 * C / 2) * 2);
+    p.add("IO", M * (C / 2) * 2);
+    p.add("T2", M * C * 4);
+    p.add("rowmax", 3 * M * 4);
+    p.add("qout", MQ * C * 4);
+    p.add("qout_b", MQ * C * 2);
+    p.add("cg", 3 * (size_t)B * C * 4);
+    // merge + neck (NHWC bf16)
+    p.add("x2", M * C * 2);
+    p.add("x3", M * C * 2);
+    p.add("x4", M * C * 2);
+    p.add("D4a", (size_t)B * g2 * g2 * h.d4() * 2);
+    p.add("D4b", (size_t)B * g4 * g4 * (h.d4() / 2) * 2);
+    p.add("P4", (size_t)B * g4 * g4 * h.d.out_dims[0] * 2);
+    p.add("D8a", (size_t)B * g2 * g2 * h.d8() * 2);
+    p.add("P8", (size_t)B * g2 * g2 * h.d.out_dims[1] * 2);
+    p.add("P16", M * h.d.out_dims[2] * 2);
+    p.add("D32a", (size_t)B * gh * gh * h.d32() * 2);
+    p.add("P32", (size_t)B * gh * gh * h.d.out_dims[3] * 2);
+    p.add("gn_partial", (size_t)B * GN_MAX_CHUNKS * 8);
+    p.add("gn_stats", (size_t)B * 8);
+    // head
+    const size_t res[4] = {g4, g2, g, gh};
+    for (int i = 0; i < 4; ++i) {
+        p.add(("HC" + std::to_string(i)).c_str(), (size_t)B * res[i] * res[i] * hc * 2);
+        p.add(("Y" + std::to_string(i)).c_str(), (size_t)B * res[i] * res[i] * hc * 2);
+    }
+    p.add("F", (size_t)B * g4 * g4 * hc * 2);
+    p.add("rnorm", (size_t)B * g4 * g4 * 4);
+    p.add("QF", MQ * 2 * C * 2);
+    p.add("QE", MQ * hc * 4);
+    p.add("QN", (size_t)B * 64 * hc * 2);
+    p.add("seg_low", (size_t)B * g4 * g4 * 4);
+    p.add("aux_low", (size_t)B * Q * g4 * g4 * 4);
+    p.total = (p.total + 1023) & ~size_t(1023);
+    return p;
+}
+
+struct Fwd {
+    vpu_context& h;
+    cudaStream_t s;
+    uint8_t* ws;
+    Plan plan;
+    int B;
+
+    template <typename T> T* buf(const char* name) { return reinterpret_cast<T*>(ws + plan.find(name)->off); }
+    template <typename T> const T* W(const std::string& key) { return reinterpret_cast<const T*>(h.w.at(key).p); }
+    const __nv_bfloat16* Wb(const std::string& key) { return W<__nv_bfloat16>(key); }
+    const float* Wf(const std::string& key) { return W<float>(key); }
+
+    // out = act(A W^T + bias [+ tab] [+ res])
+    int gemm(const __nv_bfloat16* A, int lda, const std::string& wkey, int M, int Nn, int K, const float* bias, void* out,
+             bool out_bf16, int ldo, int act = ACT_NONE, const void* res = nullptr, bool res_bf16 = false, int ldr = 0,
+             const float* tab = nullptr, int tab_rows = 0) {
+        GemmProblem p;
+        p.A = A; p.W = Wb(wkey); p.M = M; p.N = Nn; p.K = K; p.lda = lda;
+        p.ldw = (int)h.w.at(wkey).shape[1];
+        p.w_rows = Nn;
+        p.epi.out = out; p.epi.out_bf16 = out_bf16; p.epi.ldo = ldo; p.epi.bias = bias; p.epi.act = act;
+        p.epi.res = res; p.epi.res_bf16 = res_bf16; p.epi.ldr = ldr; p.epi.bias2d = tab; p.epi.bias2d_rows = tab_rows;
+        return gemm_launch(p, s, h.gemm_impl);
+    }
+    int gemm_ps(const __nv_bfloat16* A, const std::string& wkey, const float* bias4, int M, int cout, int K, int g,
+                __nv_bfloat16* out) {
+        GemmProblem p;
+        p.A = A; p.W = Wb(wkey); p.M = M; p.N = 4 * cout; p.K = K; p.lda = K; p.ldw = K; p.w_rows = 4 * cout;
+        p.epi.out = out; p.epi.out_bf16 = 1; p.epi.ldo = cout; p.epi.bias = bias4; p.epi.mode = EPI_PIXEL_SHUFFLE;
+        p.epi.ps_g = g; p.epi.ps_cout = cout;
+        return gemm_launch(p, s, h.gemm_impl);
+    }
+    int ln(const float* in, const std::string& key, float eps, int rows, float* of, __nv_bfloat16* ob,
+           const float* pe = nullptr, __nv_bfloat16* ope = nullptr, float* rowmax = nullptr) {
+        LnArgs a;
+        a.in = in; a.gamma = Wf(key + ".g"); a.beta = Wf(key + ".b"); a.eps = eps; a.rows = rows;
+        a.out_f32 = of; a.out_bf16 = ob; a.pe = pe; a.out_pe_bf16 = ope; a.rowmax = rowmax;
+        return layernorm_launch(a, h.C(), s);
+    }
+    int gn(__nv_bfloat16* x, size_t per_sample, int Cc, const std::string& key, int gelu) {
+        return groupnorm_launch(x, B, per_sample, Cc, Wf(key + ".g"), Wf(key + ".b"), gelu, buf<float2>("gn_partial"),
+                                buf<float2>("gn_stats"), s);
+    }
+    int attn(const __nv_bfloat16* q, int ldq, int qoff, const __nv_bfloat16* k, int ldk, int koff, const __nv_bfloat16* v,
+             int ldv, int voff, __nv_bfloat16* o, int ldo, int Sq, int Sk, int heads, int hd, int nprob, float scale,
+             bool windowed) {
+        AttnArgs a;
+        a.q = q; a.k = k; a.v = v; a.o = o; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+        a.qoff = qoff; a.koff = koff; a.voff = voff; a.Sq = Sq; a.Sk = Sk; a.heads = heads; a.nprob = nprob;
+        a.scale_log2 = scale * 1.4426950408889634f;
+        if (windowed) {
+            a.qmap.mode = 1; a.qmap.tokens = h.N(); a.qmap.grid = h.grid(); a.qmap.win = 224 / h.d.patch;
+            a.kmap = a.qmap;
+        } else {
+            a.qmap.mode = 0; a.qmap.per_prob = Sq;
+            a.kmap.mode = 0; a.kmap.per_prob = Sk;
+        }
+        return attention_launch(a, hd, s);
+    }
+};
+
+#define RUN(x)                  \
+    do {                        \
+        if (int _rc = (x)) return _rc; \
+    } while (0)
+
+int fill_ppue_args(const vpu_context& h, const vpu_prompts& pr, PpueArgs& a) {
+    const bool own = pr.type != 0 && pr.ppue_points != nullptr;
+    a.points = own ? pr.ppue_points : pr.points;
+    a.n = own ? pr.n_ppue : pr.n;
+    a.num_max_points = h.d.num_max_points;
+    a.size = h.d.img_size;
+    a.type = pr.type;
+    a.boxes = pr.boxes; a.scrib_sel = pr.scrib_sel; a.scrib_slot = pr.scrib_slot;
+    a.click_radius = h.click_radius;
+    memcpy(a.click_table, h.click_table, sizeof(a.click_table));
+    VPU_REQUIRE(a.points != nullptr, "prompts.points is NULL");
+    VPU_REQUIRE(pr.type >= 0 && pr.type <= 2, "as_prompt_type %d not in {0,1,2}", pr.type);
+    return 0;
+}
+
+int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int B, float* instances, float* aux,
+                uint8_t* ws, cudaStream_t s) {
+    Fwd f{h, s, ws, make_plan(h, B), B};
+    const int C = h.C(), N = h.N(), M = B * N, Q = h.Q(), MQ = B * Q, g = h.grid(), img = h.d.img_size;
+    const int heads = h.d.num_heads, hd = C / heads;
+    typedef __nv_bfloat16 bf;
+
+    // ---- A1-A3, A7: fused image + coord-feature patch operand, one GEMM for both patch embeds ----
+    CoordArgs ca;
+    ca.image4 = image4; ca.points = pr.points; ca.extra_mask = pr.extra_mask; ca.n = pr.n; ca.H = img; ca.W = img;
+    ca.radius = h.d.norm_radius;
+    RUN(patch_operand_launch(ca, B, f.buf<bf>("A0"), h.d.patch, h.K0(), s));
+    float* X = f.buf<float>("X");
+    RUN(f.gemm(f.buf<bf>("A0"), h.K0(), "pe.w", M, C, h.K0(), nullptr, X, false, C, ACT_NONE, nullptr, false, 0,
+               f.Wf("pe.tab"), N));
+
+    // ---- A8-A9: ViT blocks ----
+    bf* Xn = f.buf<bf>("Xn");
+    bf* QKV = f.buf<bf>("QKV");
+    bf* AO = f.buf<bf>("AO");
+    bf* Hh = f.buf<bf>("H");
+    const int win = 224 / h.d.patch, nwin = (g / win) * (g / win);
+    // parity taps only: "debug.stop_after_block" = k ends the forward after k ViT blocks (X holds the tokens)
+    const int stop_after = h.scalars.count("debug.stop_after_block") ? (int)h.scalars.at("debug.stop_after_block") : -1;
+    if (stop_after == 0) return 0;
+    for (int i = 1; i <= h.d.depth; ++i) {
+        const std::string k = "blk" + std::to_string(i - 1);
+        const bool windowed = (i % h.group()) != 0;
+        RUN(f.ln(X, k + ".ln1", 1e-6f, M, nullptr, Xn));
+        RUN(f.gemm(Xn, C, k + ".qkv.w", M, 3 * C, C, f.Wf(k + ".qkv.b"), QKV, true, 3 * C));
+        if (windowed)
+            RUN(f.attn(QKV, 3 * C, 0, QKV, 3 * C, C, QKV, 3 * C, 2 * C, AO, C, win * win, win * win, heads, hd, B * nwin,
+                       1.0f / sqrtf((float)hd), true));
+        else
+            RUN(f.attn(QKV, 3 * C, 0, QKV, 3 * C, C, QKV, 3 * C, 2 * C, AO, C, N, N, heads, hd, B, 1.0f / sqrtf((float)hd),
+                       false));
+        RUN(f.gemm(AO, C, k + ".proj.w", M, C, C, f.Wf(k + ".proj.b"), X, false, C, ACT_NONE, X, false, C));
+        RUN(f.ln(X, k + ".ln2", 1e-6f, M, nullptr, Xn));
+        RUN(f.gemm(Xn, C, k + ".fc1.w", M, 4 * C, C, f.Wf(k + ".fc1.b"), Hh, true, 4 * C, ACT_GELU));
+        RUN(f.gemm(Hh, 4 * C, k + ".fc2.w", M, C, 4 * C, f.Wf(k + ".fc2.b"), X, false, C, ACT_NONE, X, false, C));
+        if (stop_after == i) return 0;
+    }
+
+    // ---- A4-A6, A10: PPuE rows + FFN ----
+    PpueArgs pa;
+    RUN(fill_ppue_args(h, pr, pa));
+    pa.out = f.buf<float>("ppue");
+    pa.out_bf16 = f.buf<bf>("ppue_b");
+    pa.ld_bf16 = h.ppue_ld();
+    RUN(ppue_launch(pa, B, s));
+    float* Q0 = f.buf<float>("Q0");
+    RUN(f.gemm(f.buf<bf>("ppue_b"), h.ppue_ld(), "ffn.w1", MQ, h.d.ppue_ffn_dim, h.ppue_ld(), f.Wf("ffn.b1"), f.buf<bf>("T1"),
+               true, h.d.ppue_ffn_dim, ACT_RELU));
+    RUN(f.gemm(f.buf<bf>("T1"), h.d.ppue_ffn_dim, "ffn.w2", MQ, C, h.d.ppue_ffn_dim, f.Wf("ffn.b2"), Q0, false, C));
+
+    // ---- A11-A13: Dual-cross Merging Attention ----
+    bf* Q0b = f.buf<bf>("Q0b");
+    bf* Qb = f.buf<bf>("Qb");
+    bf* QPb = f.buf<bf>("QPb");
+    float* Qt = f.buf<float>("Qt");
+    float* T = f.buf<float>("T");
+    bf* X0b = f.buf<bf>("X0b");
+    bf* Kb = f.buf<bf>("Kb");
+    bf* KVQ = f.buf<bf>("KVQ");
+    float* rowmax = f.buf<float>("rowmax");
+    RUN(cast_add_launch(Q0, nullptr, Q0b, (size_t)MQ * C, s));
+    RUN(cast_add_launch(X, nullptr, X0b, (size_t)M * C, s));
+    const int dh = h.d.dma_heads, Ci = C / 2, dself = C / dh, dcross = Ci / dh;
+    const float* Qf = Q0;  // current fp32 queries
+    const bf* Kin = X0b;   // current bf16 keys
+    float* ql[3] = {f.buf<float>("ql0"), f.buf<float>("ql1"), f.buf<float>("ql2")};
+    for (int j = 0; j < h.d.dma_depth; ++j) {
+        const std::string k = "dma" + std::to_string(j);
+        // (1) prompt self-attention (layer 0: no PE, output replaces the queries; transformer.py:436-442)
+        const bf* qk_in = j == 0 ? Q0b : QPb;
+        const bf* v_in = j == 0 ? Q0b : Qb;
+        RUN(f.gemm(qk_in, C, k + ".sa.qk.w", MQ, 2 * C, C, f.Wf(k + ".sa.qk.b"), f.buf<bf>("SQK"), true, 2 * C));
+        RUN(f.gemm(v_in, C, k + ".sa.v.w", MQ, C, C, f.Wf(k + ".sa.v.b"), f.buf<bf>("SV"), true, C));
+        RUN(f.attn(f.buf<bf>("SQK"), 2 * C, 0, f.buf<bf>("SQK"), 2 * C, C, f.buf<bf>("SV"), C, 0, f.buf<bf>("SO"), C, Q, Q, dh,
+                   dself, B, 1.0f / sqrtf((float)dself), false));
+        RUN(f.gemm(f.buf<bf>("SO"), C, k + ".sa.o.w", MQ, C, C, f.Wf(k + ".sa.o.b"), T, false, C, ACT_NONE,
+                   j == 0 ? nullptr : Qf, false, C));
+        RUN(f.ln(T, k + ".n1", 1e-5f, MQ, Qt, Qb, Q0, QPb));
+        Qf = Qt;
+        // (2) tokens -> image cross attention; the image-side K|V (and step 4's Q) come from one GEMM whose
+        //     positional term key_pe W^T is a precomputed additive table (transformer.py:444-449)
+        RUN(f.gemm(QPb, C, k + ".t2i.q.w", MQ, Ci, C, f.Wf(k + ".t2i.q.b"), f.buf<bf>("TQ"), true, Ci));
+        RUN(f.gemm(Kin, C, k + ".img.w", M, 3 * Ci, C, nullptr, KVQ, true, 3 * Ci, ACT_NONE, nullptr, false, 0,
+                   f.Wf(k + ".img.tab"), N));
+        RUN(f.attn(f.buf<bf>("TQ"), Ci, 0, KVQ, 3 * Ci, 0, KVQ, 3 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
+                   1.0f / sqrtf((float)dcross), false));
+        RUN(f.gemm(f.buf<bf>("TO"), Ci, k + ".t2i.o.w", MQ, C, Ci, f.Wf(k + ".t2i.o.b"), T, false, C, ACT_NONE, Qf, false, C));
+        RUN(f.ln(T, k + ".n2", 1e-5f, MQ, Qt, Qb, Q0, QPb));
+        // (3) MLP (transformer.py:451-454)
+        RUN(f.gemm(Qb, C, k + ".mlp.w1", MQ, h.d.dma_mlp_dim, C, f.Wf(k + ".mlp.b1"), f.buf<bf>("MH"), true, h.d.dma_mlp_dim,
+                   ACT_RELU));
+        RUN(f.gemm(f.buf<bf>("MH"), h.d.dma_mlp_dim, k + ".mlp.w2", MQ, C, h.d.dma_mlp_dim, f.Wf(k + ".mlp.b2"), T, false, C,
+                   ACT_NONE, Qf, false, C));
+        RUN(f.ln(T, k + ".n3", 1e-5f, MQ, ql[j], Qb, Q0, QPb));
+        Qf = ql[j];
+        // (4) image -> tokens cross attention (transformer.py:456-461)
+        RUN(f.gemm(QPb, C, k + ".i2t.k.w", MQ, Ci, C, f.Wf(k + ".i2t.k.b"), f.buf<bf>("IK"), true, Ci));
+        RUN(f.gemm(Qb, C, k + ".i2t.v.w", MQ, Ci, C, f.Wf(k + ".i2t.v.b"), f.buf<bf>("IV"), true, Ci));
+        RUN(f.attn(KVQ, 3 * Ci, 2 * Ci, f.buf<bf>("IK"), Ci, 0, f.buf<bf>("IV"), Ci, 0, f.buf<bf>("IO"), Ci, N, Q, dh, dcross, B,
+                   1.0f / sqrtf((float)dcross), false));
+        RUN(f.gemm(f.buf<bf>("IO"), Ci, k + ".i2t.o.w", M, C, Ci, f.Wf(k + ".i2t.o.b"), f.buf<float>("T2"), false, C, ACT_NONE,
+                   Kin, true, C));
+        RUN(f.ln(f.buf<float>("T2"), k + ".n4", 1e-5f, M, nullptr, Kb, nullptr, nullptr, rowmax + (size_t)j * M));
+        Kin = Kb;
+    }
+    // final tokens -> image attention (transformer.py:374-379)
+    RUN(f.gemm(QPb, C, "dmaf.q.w", MQ, Ci, C, f.Wf("dmaf.q.b"), f.buf<bf>("TQ"), true, Ci));
+    RUN(f.gemm(Kin, C, "dmaf.img.w", M, 2 * Ci, C, nullptr, KVQ, true, 2 * Ci, ACT_NONE, nullptr, false, 0,
+               f.Wf("dmaf.img.tab"), N));
+    RUN(f.attn(f.buf<bf>("TQ"), Ci, 0, KVQ, 2 * Ci, 0, KVQ, 2 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
+               1.0f / sqrtf((float)dcross), false));
+    RUN(f.gemm(f.buf<bf>("TO"), Ci, "dmaf.o.w", MQ, C, Ci, f.Wf("dmaf.o.b"), T, false, C, ACT_NONE, Qf, false, C));
+    RUN(f.ln(T, "dmaf.n", 1e-5f, MQ, f.buf<float>("qfin"), nullptr));
+
+    // ---- A14: merge ----
+    RUN(qout_gate_launch(Q0, ql[0], ql[1], f.buf<float>("qfin"), B, Q, C, f.buf<float>("qout"), f.buf<bf>("qout_b"),
+                         f.buf<float>("cg"), s));
+    MergeArgs ma;
+    ma.x = X; ma.cg = f.buf<float>("cg"); ma.rowmax = rowmax; ma.x2 = f.buf<bf>("x2"); ma.x3 = f.buf<bf>("x3");
+    ma.x4_s2d = f.buf<bf>("x4"); ma.B = B; ma.N = N; ma.M = M; ma.C = C; ma.grid = g;
+    RUN(merge_launch(ma, s));
+
+    // ---- A15: 4-scale pyramid (NHWC bf16; ConvT/Conv with stride == kernel are plain GEMMs) ----
+    const int d4 = h.d4(), d8 = h.d8(), d32 = h.d32();
+    const int* od = h.d.out_dims;
+    const size_t g2 = 2 * g, g4 = 4 * g, gh = g / 2;
+    RUN(f.gemm_ps(X0b, "d4.a.w", f.Wf("d4.a.b"), M, d4, C, g, f.buf<bf>("D4a")));
+    RUN(f.gn(f.buf<bf>("D4a"), g2 * g2 * d4, d4, "d4.gn1", 1));
+    RUN(f.gemm_ps(f.buf<bf>("D4a"), "d4.b.w", f.Wf("d4.b.b"), (int)(B * g2 * g2), d4 / 2, d4, (int)g2, f.buf<bf>("D4b")));
+    RUN(f.gn(f.buf<bf>("D4b"), g4 * g4 * (d4 / 2), d4 / 2, "d4.gn2", 0));
+    RUN(f.gemm(f.buf<bf>("D4b"), d4 / 2, "d4.c.w", (int)(B * g4 * g4), od[0], d4 / 2, f.Wf("d4.c.b"), f.buf<bf>("P4"), true, od[0]));
+    RUN(f.gn(f.buf<bf>("P4"), g4 * g4 * od[0], od[0], "d4.gn3", 1));
+
+    RUN(f.gemm_ps(f.buf<bf>("x2"), "d8.a.w", f.Wf("d8.a.b"), M, d8, C, g, f.buf<bf>("D8a")));
+    RUN(f.gn(f.buf<bf>("D8a"), g2 * g2 * d8, d8, "d8.gn1", 0));
+    RUN(f.gemm(f.buf<bf>("D8a"), d8, "d8.b.w", (int)(B * g2 * g2), od[1], d8, f.Wf("d8.b.b"), f.buf<bf>("P8"), true, od[1]));
+    RUN(f.gn(f.buf<bf>("P8"), g2 * g2 * od[1], od[1], "d8.gn2", 1));
+
+    RUN(f.gemm(f.buf<bf>("x3"), C, "d16.a.w", M, od[2], C, f.Wf("d16.a.b"), f.buf<bf>("P16"), true, od[2]));
+    RUN(f.gn(f.buf<bf>("P16"), (size_t)N * od[2], od[2], "d16.gn1", 1));
+
+    RUN(f.gemm(f.buf<bf>("x4"), 4 * C, "d32.a.w", (int)(B * gh * gh), d32, 4 * C, f.Wf("d32.a.b"), f.buf<bf>("D32a"), true, d32));
+    RUN(f.gn(f.buf<bf>("D32a"), gh * gh * d32, d32, "d32.gn1", 0));
+    RUN(f.gemm(f.buf<bf>("D32a"), d32, "d32.b.w", (int)(B * gh * gh), od[3], d32, f.Wf("d32.b.b"), f.buf<bf>("P32"), true, od[3]));
+    RUN(f.gn(f.buf<bf>("P32"), gh * gh * od[3], od[3], "d32.gn2", 1));
+
+    // ---- A16: head ----
+    const int hc = h.d.head_channels;
+    const char* pyr[4] = {"P4", "P8", "P16", "P32"};
+    const size_t res[4] = {g4, g2, (size_t)g, gh};
+    HeadCombineArgs hca;
+    for (int i = 0; i < 4; ++i) {
+        const std::string si = std::to_string(i);
+        const int rows = (int)(B * res[i] * res[i]);
+        RUN(f.gemm(f.buf<bf>(pyr[i]), od[i], "hd.c" + si + ".w", rows, hc, od[i], f.Wf("hd.c" + si + ".b"),
+                   f.buf<bf>(("HC" + si).c_str()), true, hc, ACT_RELU));
+        RUN(f.gemm(f.buf<bf>(("HC" + si).c_str()), hc, "hd.f" + si + ".w", rows, hc, hc, nullptr, f.buf<bf>(("Y" + si).c_str()),
+                   true, hc));
+        hca.y[i] = f.buf<bf>(("Y" + si).c_str());
+        hca.res[i] = (int)res[i];
+    }
+    hca.bias = f.Wf("hd.f.b"); hca.out = f.buf<bf>("F"); hca.rnorm = f.buf<float>("rnorm"); hca.B = B;
+    RUN(head_combine_launch(hca, s));
+    RUN(f.gemm(f.buf<bf>("qout_b"), C, "hd.q.w1", MQ, 2 * C, C, f.Wf("hd.q.b1"), f.buf<bf>("QF"), true, 2 * C, ACT_RELU));
+    RUN(f.gemm(f.buf<bf>("QF"), 2 * C, "hd.q.w2", MQ, hc, 2 * C, f.Wf("hd.q.b2"), f.buf<float>("QE"), false, hc));
+    RUN(head_queries_launch(f.buf<float>("QE"), f.Wf("hd.seg.w"), B, Q, f.buf<bf>("QN"), s));
+    {
+        GemmProblem p;
+        p.A = f.buf<bf>("F"); p.W = f.buf<bf>("QN"); p.M = (int)(B * g4 * g4); p.N = 64; p.K = hc; p.lda = hc; p.ldw = hc;
+        p.w_rows = B * 64;
+        p.epi.mode = EPI_HEAD_FINAL; p.epi.m_per_batch = (int)(g4 * g4); p.epi.b_rows_per_batch = 64;
+        p.epi.rnorm = f.buf<float>("rnorm"); p.epi.aux_out = aux ? f.buf<float>("aux_low") : nullptr;
+        p.epi.seg_out = f.buf<float>("seg_low"); p.epi.seg_bias = h.scalars.at("hd.seg.b"); p.epi.nq = Q;
+        RUN(gemm_launch(p, s, h.gemm_impl));
+    }
+    // ---- A17: final upsampling (align_corners=True) ----
+    RUN(upsample_ac_launch(f.buf<float>("seg_low"), instances, (int)g4, (int)g4, img, img, (size_t)B, s));
+    if (aux) RUN(upsample_ac_launch(f.buf<float>("aux_low"), aux, (int)g4, (int)g4, img, img, (size_t)B * Q, s));
+    return 0;
+}
+
+struct Need {
+    std::string key;
+    int dtype;
+    std::vector<int64_t> shape;
+};
+
+std::vector<Need> needed_weights(const vpu_context& h) {
+    std::vector<Need> v;
+    const int64_t C = h.C(), N = h.N(), Ci = C / 2;
+    auto lin = [&](const std::string& k, int64_t o, int64_t i) {
+        v.push_back({k + ".w", VPU_BF16, {o, i}});
+        v.push_back({k + ".b", VPU_F32, {o}});
+    };
+    auto lin2 = [&](const std::string& k, const char* s, int64_t o, int64_t i) {  // key.w1/.b1 style
+        v.push_back({k + ".w" + s, VPU_BF16, {o, i}});
+        v.push_back({k + ".b" + s, VPU_F32, {o}});
+    };
+    auto nrm = [&](const std::string& k, int64_t c) {
+        v.push_back({k + ".g", VPU_F32, {c}});
+        v.push_back({k + ".b", VPU_F32, {c}});
+    };
+    v.push_back({"pe.w", VPU_BF16, {C, h.K0()}});
+    v.push_back({"pe.tab", VPU_F32, {N, C}});
+    for (int i = 0; i < h.d.depth; ++i) {
+        const std::string k = "blk" + std::to_string(i);
+        nrm(k + ".ln1", C); nrm(k + ".ln2", C);
+        lin(k + ".qkv", 3 * C, C); lin(k + ".proj", C, C); lin(k + ".fc1", 4 * C, C); lin(k + ".fc2", C, 4 * C);
+    }
+    lin2("ffn", "1", h.d.ppue_ffn_dim, h.ppue_ld());
+    lin2("ffn", "2", C, h.d.ppue_ffn_dim);
+    for (int j = 0; j < h.d.dma_depth; ++j) {
+        const std::string k = "dma" + std::to_string(j);
+        lin(k + ".sa.qk", 2 * C, C); lin(k + ".sa.v", C, C); lin(k + ".sa.o", C, C); nrm(k + ".n1", C);
+        lin(k + ".t2i.q", Ci, C);
+        v.push_back({k + ".img.w", VPU_BF16, {3 * Ci, C}});
+        v.push_back({k + ".img.tab", VPU_F32, {N, 3 * Ci}});
+        lin(k + ".t2i.o", C, Ci); nrm(k + ".n2", C);
+        lin2(k + ".mlp", "1", h.d.dma_mlp_dim, C); lin2(k + ".mlp", "2", C, h.d.dma_mlp_dim); nrm(k + ".n3", C);
+        lin(k + ".i2t.k", Ci, C); lin(k + ".i2t.v", Ci, C); lin(k + ".i2t.o", C, Ci); nrm(k + ".n4", C);
+    }
+    lin("dmaf.q", Ci, C);
+    v.push_back({"dmaf.img.w", VPU_BF16, {2 * Ci, C}});
+    v.push_back({"dmaf.img.tab", VPU_F32, {N, 2 * Ci}});
+    lin("dmaf.o", C, Ci); nrm("dmaf.n", C);
+    const int64_t d4 = h.d4(), d8 = h.d8(), d32 = h.d32();
+    const int* od = h.d.out_dims;
+    lin("d4.a", 4 * d4, C); nrm("d4.gn1", d4); lin("d4.b", 4 * (d4 / 2), d4); nrm("d4.gn2", d4 / 2);
+    lin("d4.c", od[0], d4 / 2); nrm("d4.gn3", od[0]);
+    lin("d8.a", 4 * d8, C); nrm("d8.gn1", d8); lin("d8.b", od[1], d8); nrm("d8.gn2", od[1]);
+    lin("d16.a", od[2], C); nrm("d16.gn1", od[2]);
+    lin("d32.a", d32, 4 * C); nrm("d32.gn1", d32); lin("d32.b", od[3], d32); nrm("d32.gn2", od[3]);
+    const int64_t hc = h.d.head_channels;
+    for (int i = 0; i < 4; ++i) {
+        lin("hd.c" + std::to_string(i), hc, od[i]);
+        v.push_back({"hd.f" + std::to_string(i) + ".w", VPU_BF16, {hc, hc}});
+    }
+    v.push_back({"hd.f.b", VPU_F32, {hc}});
+    lin2("hd.q", "1", 2 * C, C);
+    lin2("hd.q", "2", hc, 2 * C);
+    v.push_back({"hd.seg.w", VPU_F32, {hc}});
+    return v;
+}
+
+bool valid_handle(vpu_handle h) {
+    if (!h) { set_error("null handle"); return false; }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vpu_last_error(void) { return vpu::last_error(); }
+int vpu_version(void) { return 1; }
+
+int vpu_create(vpu_handle* out, const vpu_dims* dims) {
+    VPU_REQUIRE(out && dims, "vpu_create: null argument");
+    const vpu_dims& d = *dims;
+    VPU_REQUIRE(d.img_size > 0 && d.patch > 0 && d.img_size % d.patch == 0, "bad image/patch size");
+    VPU_REQUIRE(d.embed_dim == 768 || d.embed_dim == 1024 || d.embed_dim == 1280, "embed_dim %d not in {768,1024,1280}", d.embed_dim);
+    VPU_REQUIRE(d.depth % 4 == 0, "depth must be a multiple of 4 (reference models_vit.py:264)");
+    VPU_REQUIRE(d.embed_dim % d.num_heads == 0 && d.embed_dim % (2 * d.dma_heads) == 0, "head counts must divide embed_dim");
+    VPU_REQUIRE(d.head_channels == 256, "head_channels must be 256 (upsample='x1')");
+    VPU_REQUIRE(d.num_max_points >= 1 && d.num_max_points <= 24, "num_max_points must be in [1, 24]");
+    VPU_REQUIRE((d.img_size / d.patch) % (224 / d.patch) == 0 && (d.img_size / d.patch) % 2 == 0, "grid must tile into 224-px windows");
+    vpu_context* h = new vpu_context();
+    h->d = d;
+    const char* impl = getenv("VPU_GEMM_IMPL");
+    h->gemm_impl = (impl && impl[0] == '1') ? 1 : 0;
+    // click Gaussian table: the reference's float32 formula (ops.py:51-61), sigma = 3, peak + 1
+    const int r = 9;
+    h->click_radius = r;
+    for (int k = 0; k < 32; ++k) h->click_table[k] = 0.f;
+    for (int k = 0; k <= 2 * r; ++k) {
+        const float kk = (float)k - (float)r;
+        const float sq = kk * kk;
+        h->click_table[k] = (float)std::exp((double)(-sq / 18.0f));
+    }
+    h->click_table[r] += 1.0f;
+    *out = h;
+    return 0;
+}
+
+void vpu_destroy(vpu_handle h) { delete h; }
+
+int vpu_bind_weight(vpu_handle h, const char* key, const void* dev_ptr, int dtype, const int64_t* shape, int rank) {
+    if (!valid_handle(h)) return 1;
+    VPU_REQUIRE(key && dev_ptr && rank >= 0 && rank <= 4, "vpu_bind_weight: bad argument");
+    Tensor t;
+    t.p = dev_ptr; t.dtype = dtype;
+    t.shape.assign(shape, shape + rank);
+    h->w[key] = t;
+    h->finalized = false;
+    return 0;
+}
+
+int vpu_set_scalar(vpu_handle h, const char* key, float value) {
+    if (!valid_handle(h)) return 1;
+    h->scalars[key] = value;
+    return 0;
+}
+
+int vpu_set_click_table(vpu_handle h, const float* host_table, int taps) {
+    if (!valid_handle(h)) return 1;
+    VPU_REQUIRE(host_table && taps >= 1 && taps <= 31 && (taps & 1), "click table must have an odd number of taps <= 31");
+    for (int k = 0; k < 32; ++k) h->click_table[k] = k < taps ? host_table[k] : 0.f;
+    h->click_radius = taps / 2;
+    return 0;
+}
+
+int vpu_finalize(vpu_handle h) {
+    if (!valid_handle(h)) return 1;
+    for (const Need& n : needed_weights(*h)) {
+        auto it = h->w.find(n.key);
+        VPU_REQUIRE(it != h->w.end(), "weight '%s' is not bound", n.key.c_str());
+        VPU_REQUIRE(it->second.dtype == n.dtype, "weight '%s' has dtype %d, expected %d", n.key.c_str(), it->second.dtype, n.dtype);
+        VPU_REQUIRE(it->second.shape == n.shape, "weight '%s' has the wrong shape", n.key.c_str());
+        VPU_REQUIRE((reinterpret_cast<uintptr_t>(it->second.p) & 15) == 0, "weight '%s' is not 16-byte aligned", n.key.c_str());
+    }
+    VPU_REQUIRE(h->scalars.count("hd.seg.b"), "scalar 'hd.seg.b' is not set");
+    if (int rc = gemm_init()) return rc;
+    h->finalized = true;
+    return 0;
+}
+
+size_t vpu_workspace_bytes(vpu_handle h, int B) {
+    if (!valid_handle(h) || B <= 0) return 0;
+    return make_plan(*h, B).total;
+}
+
+int vpu_workspace_lookup(vpu_handle h, int B, const char* name, size_t* offset, size_t* bytes) {
+    if (!valid_handle(h)) return 1;
+    VPU_REQUIRE(B > 0 && name && offset && bytes, "vpu_workspace_lookup: bad argument");
+    Plan p = make_plan(*h, B);
+    const Buf* b = p.find(name);
+    VPU_REQUIRE(b != nullptr, "no workspace buffer named '%s'", name);
+    *offset = b->off;
+    *bytes = b->bytes;
+    return 0;
+}
+
+static int check_prompts(vpu_handle h, const vpu_prompts* pr) {
+    VPU_REQUIRE(pr && pr->points, "prompts / prompts.points is NULL");
+    VPU_REQUIRE(pr->n >= 1 && pr->n <= h->d.num_max_points, "points per half n=%d outside [1, %d]", pr->n, h->d.num_max_points);
+    VPU_REQUIRE(pr->type >= 0 && pr->type <= 2, "as_prompt_type %d not in {0,1,2}", pr->type);
+    if (pr->type == 1) VPU_REQUIRE(pr->boxes, "as_prompt_type 1 needs boxes");
+    if (pr->type == 2) VPU_REQUIRE(pr->scrib_sel && pr->scrib_slot, "as_prompt_type 2 needs scrib_sel and scrib_slot");
+    return 0;
+}
+
+int vpu_forward(vpu_handle h, const float* image4, const vpu_prompts* prompts, int B, float* instances, float* instances_aux,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    if (!valid_handle(h)) return 1;
+    VPU_REQUIRE(h->finalized, "vpu_forward before vpu_finalize");
+    VPU_REQUIRE(image4 && instances && workspace && B > 0, "vpu_forward: null argument");
+    if (int rc = check_prompts(h, prompts)) return rc;
+    VPU_REQUIRE(workspace_bytes >= vpu_workspace_bytes(h, B), "workspace too small: %zu < %zu", workspace_bytes, vpu_workspace_bytes(h, B));
+    VPU_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    return run_forward(*h, image4, *prompts, B, instances, instances_aux, reinterpret_cast<uint8_t*>(workspace),
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_ppue(vpu_handle h, const vpu_prompts* prompts, int B, float* out, void* stream) {
+    if (!valid_handle(h)) return 1;
+    if (int rc = check_prompts(h, prompts)) return rc;
+    VPU_REQUIRE(out && B > 0, "vpu_ppue: null argument");
+    PpueArgs a;
+    if (int rc = fill_ppue_args(*h, *prompts, a)) return rc;
+    a.out = out;
+    return ppue_launch(a, B, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_coord_features(vpu_handle h, const float* image4, const vpu_prompts* prompts, int B, float* out, void* stream) {
+    if (!valid_handle(h)) return 1;
+    if (int rc = check_prompts(h, prompts)) return rc;
+    VPU_REQUIRE(image4 && out && B > 0, "vpu_coord_features: null argument");
+    CoordArgs ca;
+    ca.image4 = image4; ca.points = prompts->points; ca.extra_mask = prompts->extra_mask; ca.n = prompts->n;
+    ca.H = h->d.img_size; ca.W = h->d.img_size; ca.radius = h->d.norm_radius;
+    return coord_features_launch(ca, B, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, const float* bias2d,
+             int bias2d_rows, const void* residual, int residual_dtype, int ldr, int act, void* out, int out_dtype, int ldo,
+             int impl, void* stream) {
+    VPU_REQUIRE(A && W && out, "vpu_gemm: null argument");
+    GemmProblem p;
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A); p.W = reinterpret_cast<const __nv_bfloat16*>(W);
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.w_rows = N;
+    p.epi.out = out; p.epi.out_bf16 = out_dtype == VPU_BF16; p.epi.ldo = ldo; p.epi.bias = bias; p.epi.bias2d = bias2d;
+    p.epi.bias2d_rows = bias2d_rows; p.epi.res = residual; p.epi.res_bf16 = residual_dtype == VPU_BF16; p.epi.ldr = ldr;
+    p.epi.act = act;
+    return gemm_launch(p, reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int vpu_gemm_pixel_shuffle(const void* A, const void* W, int M, int cout, int K, const float* bias4, int g, void* out, int impl,
+                           void* stream) {
+    VPU_REQUIRE(A && W && out, "vpu_gemm_pixel_shuffle: null argument");
+    GemmProblem p;
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A); p.W = reinterpret_cast<const __nv_bfloat16*>(W);
+    p.M = M; p.N = 4 * cout; p.K = K; p.lda = K; p.ldw = K; p.w_rows = 4 * cout;
+    p.epi.out = out; p.epi.out_bf16 = 1; p.epi.ldo = cout; p.epi.bias = bias4; p.epi.mode = EPI_PIXEL_SHUFFLE;
+    p.epi.ps_g = g; p.epi.ps_cout = cout;
+    return gemm_launch(p, reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int vpu_attention(const void* q, int ldq, int qoff, const void* k, int ldk, int koff, const void* v, int ldv, int voff, void* o,
+                  int ldo, int Sq, int Sk, int heads, int head_dim, int nprob, float scale, int window, int grid, void* stream) {
+    VPU_REQUIRE(q && k && v && o, "vpu_attention: null argument");
+    AttnArgs a;
+    a.q = reinterpret_cast<const __nv_bfloat16*>(q); a.k = reinterpret_cast<const __nv_bfloat16*>(k);
+    a.v = reinterpret_cast<const __nv_bfloat16*>(v); a.o = reinterpret_cast<__nv_bfloat16*>(o);
+    a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.qoff = qoff; a.koff = koff; a.voff = voff;
+    a.Sq = Sq; a.Sk = Sk; a.heads = heads; a.nprob = nprob; a.scale_log2 = scale * 1.4426950408889634f;
+    if (window > 0) {
+        VPU_REQUIRE(grid % window == 0 && Sq == window * window && Sk == Sq, "windowed attention: Sq must equal window^2");
+        a.qmap.mode = 1; a.qmap.tokens = grid * grid; a.qmap.grid = grid; a.qmap.win = window;
+        a.kmap = a.qmap;
+    } else {
+        a.qmap.per_prob = Sq;
+        a.kmap.per_prob = Sk;
+    }
+    return attention_launch(a, head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_layernorm(const float* in, const float* gamma, const float* beta, float eps, int rows, int C, float* out_f32,
+                  void* out_bf16, const float* pe, void* out_pe_bf16, float* rowmax, void* stream) {
+    VPU_REQUIRE(in && gamma && beta, "vpu_layernorm: null argument");
+    LnArgs a;
+    a.in = in; a.gamma = gamma; a.beta = beta; a.eps = eps; a.rows = rows; a.out_f32 = out_f32;
+    a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.pe = pe;
+    a.out_pe_bf16 = reinterpret_cast<__nv_bfloat16*>(out_pe_bf16); a.rowmax = rowmax;
+    return layernorm_launch(a, C, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_groupnorm_nhwc(void* x, int B, int64_t per_sample, int C, const float* gamma, const float* beta, int gelu, void* scratch,
+                       void* stream) {
+    VPU_REQUIRE(x && gamma && beta && scratch, "vpu_groupnorm_nhwc: null argument");
+    float2* partial = reinterpret_cast<float2*>(scratch);
+    float2* stats = partial + (size_t)B * GN_MAX_CHUNKS;
+    return groupnorm_launch(reinterpret_cast<__nv_bfloat16*>(x), B, (size_t)per_sample, C, gamma, beta, gelu, partial, stats,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_upsample_align_corners(const float* in, float* out, int h, int w, int H, int W, int64_t planes, void* stream) {
+    VPU_REQUIRE(in && out, "vpu_upsample_align_corners: null argument");
+    return upsample_ac_launch(in, out, h, w, H, W, (size_t)planes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// Normalisation, merge and resampling kernels of the path (HBM-bound; warp-level reductions,
+// 16-byte vector accesses).  Each cites the reference op it implements.
+#include "elementwise.cuh"
+
+namespace vpu {
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (reference nn.LayerNorm: eps 1e-6 in the ViT, models_vit.py:126;
+// 1e-5 in the DMA blocks, transformer.py:412-422,268).  One warp per row, row kept in registers.
+// Optional fused outputs: fp32 copy, bf16 copy, bf16(y + pe) (the with_pos_embed adds of
+// transformer.py:439-458), and the per-row max of y (spatial gate of is_vpu_model.py:113-115).
+// ------------------------------------------------------------------------------------------
+template <int VEC>  // C = 128 * VEC
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= a.rows) return;
+    constexpr int C = 128 * VEC;
+    const float4* in = reinterpret_cast<const float4*>(a.in + (size_t)row * C);
+    float4 x[VEC];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        x[i] = in[lane + 32 * i];
+        sum += x[i].x + x[i].y + x[i].z + x[i].w;
+    }
+    const float mean = warp_sum(sum) * (1.0f / C);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float d0 = x[i].x - mean, d1 = x[i].y - mean, d2 = x[i].z - mean, d3 = x[i].w - mean;
+        var += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    const float rstd = rsqrtf(warp_sum(var) * (1.0f / C) + a.eps);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c4 = lane + 32 * i;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.beta) + c4);
+        float4 y;
+        y.x = (x[i].x - mean) * rstd * g.x + b.x;
+        y.y = (x[i].y - mean) * rstd * g.y + b.y;
+        y.z = (x[i].z - mean) * rstd * g.z + b.z;
+        y.w = (x[i].w - mean) * rstd * g.w + b.w;
+        mx = fmaxf(mx, fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w)));
+        if (a.out_f32) reinterpret_cast<float4*>(a.out_f32 + (size_t)row * C)[c4] = y;
+        if (a.out_bf16) {
+            uint2 o = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+            reinterpret_cast<uint2*>(a.out_bf16 + (size_t)row * C)[c4] = o;
+        }
+        if (a.out_pe_bf16) {
+            const float4 p = reinterpret_cast<const float4*>(a.pe + (size_t)row * C)[c4];
+            uint2 o = make_uint2(pack_bf16(y.x + p.x, y.y + p.y), pack_bf16(y.z + p.z, y.w + p.w));
+            reinterpret_cast<uint2*>(a.out_pe_bf16 + (size_t)row * C)[c4] = o;
+        }
+    }
+    if (a.rowmax) {
+        mx = warp_max(mx);
+        if (lane == 0) a.rowmax[row] = mx;
+    }
+}
+
+int layernorm_launch(const LnArgs& a, int C, cudaStream_t stream) {
+    VPU_REQUIRE(a.rows > 0, "layernorm: no rows");
+    const int grid = (a.rows + 7) / 8;
+    switch (C) {
+        case 768: layernorm_kernel<6><<<grid, 256, 0, stream>>>(a); break;
+        case 1024: layernorm_kernel<8><<<grid, 256, 0, stream>>>(a); break;
+        case 1280: layernorm_kernel<10><<<grid, 256, 0, stream>>>(a); break;
+        default: VPU_REQUIRE(false, "layernorm: unsupported width %d (768/1024/1280)", C);
+    }
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// out_bf16 = bf16(a (+ b)); n multiple of 4
+__global__ void __launch_bounds__(256) cast_add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       __nv_bfloat16* __restrict__ out, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 x = reinterpret_cast<const float4*>(a)[i];
+        if (b) {
+            const float4 y = reinterpret_cast<const float4*>(b)[i];
+            x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        }
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+    }
+}
+int cast_add_launch(const float* a, const float* b, __nv_bfloat16* out, size_t n, cudaStream_t stream) {
+    VPU_REQUIRE(n % 4 == 0, "cast: element count must be a multiple of 4");
+    const size_t n4 = n / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    cast_add_kernel<<<grid, 256, 0, stream>>>(a, b, out, n4);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm(1, C) (+ optional GELU) on NHWC bf16, in place (reference is_vpu_model.py:56-86:
+// nn.GroupNorm(1, C) eps 1e-5 => statistics over all C*H*W values of one sample).
+// stats: grid (chunks, B) fp32 partial sums; finalize in double; apply: elementwise.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, size_t per_sample,
+                                                       float2* __restrict__ partial) {
+    const int b = blockIdx.y, chunks = gridDim.x;
+    const uint4* p = reinterpret_cast<const uint4*>(x + (size_t)b * per_sample);
+    const size_t n8 = per_sample / 8;
+    float s = 0.f, ss = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)chunks * blockDim.x) {
+        const uint4 v = p[i];
+        const float2 a = unpack_bf16(v.x), b2 = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+        s += a.x + a.y + b2.x + b2.y + c.x + c.y + d.x + d.y;
+        ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+    }
+    __shared__ float sh[2][8];
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float S = 0.f, SS = 0.f;
+        for (int w = 0; w < 8; ++w) { S += sh[0][w]; SS += sh[1][w]; }
+        partial[(size_t)b * chunks + blockIdx.x] = make_float2(S, SS);
+    }
+}
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int chunks, double count, float eps,
+                                   float2* __restrict__ mean_rstd) {
+    const int b = blockIdx.x;
+    double s = 0.0, ss = 0.0;
+    for (int i = threadIdx.x; i < chunks; i += 32) { s += partial[(size_t)b * chunks + i].x; ss += partial[(size_t)b * chunks + i].y; }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if (threadIdx.x == 0) {
+        const double mean = s / count;
+        double var = ss / count - mean * mean;
+        if (var < 0) var = 0;
+        mean_rstd[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+}
+__global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ x, size_t per_sample, int C,
+                                                       const float2* __restrict__ mean_rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int gelu) {
+    const int b = blockIdx.y;
+    const float2 mr = mean_rstd[b];
+    uint4* p = reinterpret_cast<uint4*>(x + (size_t)b * per_sample);
+    const size_t n8 = per_sample / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)((i * 8) % C);
+        uint4 v = p[i];
+        float f[8];
+        float2 t;
+        t = unpack_bf16(v.x); f[0] = t.x; f[1] = t.y;
+        t = unpack_bf16(v.y); f[2] = t.x; f[3] = t.y;
+        t = unpack_bf16(v.z); f[4] = t.x; f[5] = t.y;
+        t = unpack_bf16(v.w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float y = (f[k] - mr.x) * mr.y * __ldg(gamma + c + k) + __ldg(beta + c + k);
+            f[k] = gelu ? gelu_erf(y) : y;
+        }
+        v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]); v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
+        p[i] = v;
+    }
+}
+int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta,
+                     int gelu, float2* partial, float2* mean_rstd, cudaStream_t stream) {
+    VPU_REQUIRE(per_sample % 8 == 0 && C % 8 == 0, "groupnorm: sizes must be multiples of 8");
+    int chunks = (int)((per_sample / 8 + 255) / 256);
+    if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+    gn_stats_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, per_sample, partial);
+    gn_finalize_kernel<<<B, 32, 0, stream>>>(partial, chunks, (double)per_sample, 1e-5f, mean_rstd);
+    gn_apply_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, per_sample, C, mean_rstd, gamma, beta, gelu);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// q_out = q + q1 + q2 + q_final and the three channel gates sigmoid(max over the 48 prompt
+// tokens) (reference is_vpu_model.py:104-108).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qout_gate_kernel(const float* __restrict__ q0, const float* __restrict__ q1,
+                                                        const float* __restrict__ q2, const float* __restrict__ q3,
+                                                        int T, int C, float* __restrict__ qout,
+                                                        __nv_bfloat16* __restrict__ qout_bf16, float* __restrict__ cg) {
+    const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x, B = gridDim.y;
+    if (c >= C) return;
+    float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+        const size_t i = ((size_t)b * T + t) * C + c;
+        const float a1 = q1[i], a2 = q2[i], a3 = q3[i];
+        m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+        const float s = q0[i] + a1 + a2 + a3;
+        qout[i] = s;
+        qout_bf16[i] = __float2bfloat16(s);
+    }
+    cg[((size_t)0 * B + b) * C + c] = 1.0f / (1.0f + expf(-m1));
+    cg[((size_t)1 * B + b) * C + c] = 1.0f / (1.0f + expf(-m2));
+    cg[((size_t)2 * B + b) * C + c] = 1.0f / (1.0f + expf(-m3));
+}
+int qout_gate_launch(const float* q0, const float* q1, const float* q2, const float* q3, int B, int T, int C, float* qout,
+                     __nv_bfloat16* qout_bf16, float* cg, cudaStream_t stream) {
+    qout_gate_kernel<<<dim3((C + 127) / 128, B), 128, 0, stream>>>(q0, q1, q2, q3, T, C, qout, qout_bf16, cg);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// DMA merge (reference is_vpu_model.py:109-126): x_l = x + x*cg_l[b,c] + x*sg_l[b,token],
+// sg = sigmoid(rowmax of keys_l).  One pass writes bf16 x0 (un-merged, for down_4), x2, x3 and
+// x4 in the space-to-depth layout the 2x2/stride-2 conv of down_32 consumes as a plain GEMM.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
+    const int C4 = a.C / 4;
+    const size_t total = (size_t)a.M * C4;
+    const int g = a.grid, gh = g / 2;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(idx / C4), c = (int)(idx % C4) * 4;
+        const int b = m / a.N, tok = m % a.N;
+        const float4 x = reinterpret_cast<const float4*>(a.x)[idx];
+        auto gate = [&](int l) {
+            const float4 cgv = *reinterpret_cast<const float4*>(a.cg + ((size_t)l * a.B + b) * a.C + c);
+            const float sg = 1.0f / (1.0f + expf(-a.rowmax[(size_t)l * a.M + m]));
+            return make_float4(x.x + x.x * cgv.x + x.x * sg, x.y + x.y * cgv.y + x.y * sg, x.z + x.z * cgv.z + x.z * sg,
+                               x.w + x.w * cgv.w + x.w * sg);
+        };
+        auto st = [&](__nv_bfloat16* dst, size_t off, const float4& v) {
+            *reinterpret_cast<uint2*>(dst + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        };
+        st(a.x0, (size_t)m * a.C + c, x);
+        st(a.x2, (size_t)m * a.C + c, gate(0));
+        st(a.x3, (size_t)m * a.C + c, gate(1));
+        const int i = tok / g, j = tok % g;
+        const size_t orow = (size_t)b * gh * gh + (size_t)(i / 2) * gh + j / 2;
+        st(a.x4_s2d, orow * 4 * a.C + (size_t)((i & 1) * 2 + (j & 1)) * a.C + c, gate(2));
+    }
+}
+int merge_launch(const MergeArgs& a, cudaStream_t stream) {
+    VPU_REQUIRE(a.C % 4 == 0 && a.grid % 2 == 0, "merge: bad geometry");
+    const size_t total = (size_t)a.M * (a.C / 4);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    merge_kernel<<<grid, 256, 0, stream>>>(a);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Head combine.  Reference swin_transformer.py:727-737: four (1x1 conv + ReLU) maps are resized
+// (bilinear, align_corners=False) to the 1/4 scale, concatenated and passed through the fusion
+// 1x1 conv + ReLU.  A 1x1 conv mixes channels per pixel and bilinear resizing mixes pixels per
+// channel, so they commute: fusion(cat_i resize(h_i)) = sum_i resize(W_i h_i).  The GEMMs produce
+// y_i = W_i h_i at native resolution; this kernel forms relu(b + y_0 + sum_i resize(y_i)) without
+// ever materialising the 1024-channel concat, and emits 1/max(||f||, 1e-12) per pixel for the
+// P2CL cosine logits (F.normalize, swin_transformer.py:751).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(int dst, int in, int out, int& i0, int& i1, float& lam) {
+    float s = ((float)dst + 0.5f) * ((float)in / (float)out) - 0.5f;   // align_corners=False
+    if (s < 0.f) s = 0.f;
+    i0 = (int)s;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    lam = s - (float)i0;
+}
+__device__ __forceinline__ void acc8(float (&f)[8], const __nv_bfloat16* p, float w) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    float2 t;
+    t = unpack_bf16(v.x); f[0] += w * t.x; f[1] += w * t.y;
+    t = unpack_bf16(v.y); f[2] += w * t.x; f[3] += w * t.y;
+    t = unpack_bf16(v.z); f[4] += w * t.x; f[5] += w * t.y;
+    t = unpack_bf16(v.w); f[6] += w * t.x; f[7] += w * t.y;
+}
+// one warp per output pixel, 256 channels = 8 per lane
+__global__ void __launch_bounds__(256) head_combine_kernel(const HeadCombineArgs a) {
+    const size_t pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int R = a.res[0];
+    if (pix >= (size_t)a.B * R * R) return;
+    const int b = (int)(pix / ((size_t)R * R)), yx = (int)(pix % ((size_t)R * R)), y = yx / R, x = yx % R;
+    const int c = lane * 8;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = __ldg(a.bias + c + k);
+    acc8(f, a.y[0] + pix * 256 + c, 1.0f);
+#pragma unroll
+    for (int l = 1; l < 4; ++l) {
+        const int r = a.res[l];
+        int y0, y1, x0, x1;
+        float ly, lx;
+        src_index(y, r, R, y0, y1, ly);
+        src_index(x, r, R, x0, x1, lx);
+        const __nv_bfloat16* base = a.y[l] + (size_t)b * r * r * 256 + c;
+        acc8(f, base + ((size_t)y0 * r + x0) * 256, (1.f - ly) * (1.f - lx));
+        acc8(f, base + ((size_t)y0 * r + x1) * 256, (1.f - ly) * lx);
+        acc8(f, base + ((size_t)y1 * r + x0) * 256, ly * (1.f - lx));
+        acc8(f, base + ((size_t)y1 * r + x1) * 256, ly * lx);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { f[k] = fmaxf(f[k], 0.f); ss += f[k] * f[k]; }
+    ss = warp_sum(ss);
+    *reinterpret_cast<uint4*>(a.out + pix * 256 + c) =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    if (lane == 0) a.rnorm[pix] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+}
+int head_combine_launch(const HeadCombineArgs& a, cudaStream_t stream) {
+    const size_t npix = (size_t)a.B * a.res[0] * a.res[0];
+    head_combine_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, stream>>>(a);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// P2CL queries (reference swin_transformer.py:745,750): L2-normalise the FFN output rows and lay
+// out the per-sample B operand [64, 256] of the head-final GEMM: rows 0..nq-1 = normalised
+// queries, row nq = conv_seg weight, remaining rows zero.
+__global__ void __launch_bounds__(256) head_queries_kernel(const float* __restrict__ qe, const float* __restrict__ wseg,
+                                                           int nq, __nv_bfloat16* __restrict__ out) {
+    const int b = blockIdx.x, r = blockIdx.y, c = threadIdx.x;  // 256 channels
+    __shared__ float sh[8];
+    float v = 0.f, scale = 1.f;
+    if (r < nq) {
+        v = qe[((size_t)b * nq + r) * 256 + c];
+        float ss = warp_sum(v * v);
+        if ((c & 31) == 0) sh[c >> 5] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int w = 0; w < 8; ++w) tot += sh[w];
+        scale = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    } else if (r == nq) {
+        v = wseg[c];
+    }
+    out[((size_t)b * 64 + r) * 256 + c] = __float2bfloat16(v * scale);
+}
+int head_queries_launch(const float* qe, const float* wseg, int B, int nq, __nv_bfloat16* out, cudaStream_t stream) {
+    VPU_REQUIRE(nq < 64, "head queries: nq must be < 64");
+    head_queries_kernel<<<dim3(B, 64), 256, 0, stream>>>(qe, wseg, nq, out);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Final bilinear upsampling, align_corners=True (reference is_vpu_model.py:431-436).
+// in [planes, h, w] fp32 -> out [planes, H, W] fp32; each thread writes 4 consecutive x.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                          int H, int W, size_t planes) {
+    const int W4 = W / 4;
+    const size_t total = planes * H * W4;
+    const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x4 = (int)(idx % W4);
+        const int y = (int)((idx / W4) % H);
+        const size_t pl = idx / ((size_t)W4 * H);
+        const float fy = sy * (float)y;
+        const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+        const float ly = fy - (float)y0;
+        const float* r0 = in + (pl * h + y0) * w;
+        const float* r1 = in + (pl * h + y1) * w;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float fx = sx * (float)(x4 * 4 + k);
+            const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
+            const float lx = fx - (float)x0;
+            o[k] = (1.f - ly) * ((1.f - lx) * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) +
+                   ly * ((1.f - lx) * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+        }
+        reinterpret_cast<float4*>(out)[idx] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+int upsample_ac_launch(const float* in, float* out, int h, int w, int H, int W, size_t planes, cudaStream_t stream) {
+    VPU_REQUIRE(W % 4 == 0, "upsample: output width must be a multiple of 4");
+    const size_t total = planes * H * (W / 4);
+    size_t grid = (total + 255) / 256;
+    if (grid > 148 * 32) grid = 148 * 32;
+    upsample_ac_kernel<<<(unsigned)grid, 256, 0, stream>>>(in, out, h, w, H, W, planes);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vpu

@@ -1,0 +1,50 @@
+// GEMM interface shared by the forward orchestration and the C-ABI test entry points.
+//   out[m, n] = epilogue( sum_k A[m, k] * W[n, k] )      A: bf16 [M, K] row-major, W: bf16 [N, K]
+// (the nn.Linear / 1x1-conv convention of the reference, so packed weights keep their layout).
+#pragma once
+#include "common.cuh"
+
+namespace vpu {
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+enum { EPI_PLAIN = 0, EPI_PIXEL_SHUFFLE = 1, EPI_HEAD_FINAL = 2 };
+
+struct Epi {
+    void* out = nullptr;            // [rows, ldo]; fp32 or bf16
+    int out_bf16 = 1;
+    int ldo = 0;
+    const float* bias = nullptr;    // [N]
+    const float* bias2d = nullptr;  // [bias2d_rows, N], row = m % bias2d_rows (positional tables)
+    int bias2d_rows = 0;
+    const void* res = nullptr;      // residual [M, ldr], fp32 or bf16, added before the activation is NOT
+    int res_bf16 = 0;               //   applied (act and res are never combined on this path)
+    int ldr = 0;
+    int act = ACT_NONE;
+    int mode = EPI_PLAIN;
+    // EPI_PIXEL_SHUFFLE: ConvTranspose2d(k=2,s=2) as a GEMM with N = 4*cout ordered (kh, kw, co):
+    // input row m = (b, i, j) on a g x g grid goes to output row (b, 2i+kh, 2j+kw), column co.
+    int ps_g = 0, ps_cout = 0;
+    // EPI_HEAD_FINAL: per-sample B operand (rows [b*b_rows_per_batch, +N)), NCHW fp32 stores:
+    // n < nq : aux[b, n, pix] = (acc * rnorm[m] + 1) / 2 ;  n == nq : seg[b, pix] = acc + seg_bias
+    int m_per_batch = 0, b_rows_per_batch = 0;
+    const float* rnorm = nullptr;
+    float* aux_out = nullptr;
+    float* seg_out = nullptr;
+    float seg_bias = 0.f;
+    int nq = 0;
+};
+
+struct GemmProblem {
+    const __nv_bfloat16* A = nullptr;  // [M, lda]
+    const __nv_bfloat16* W = nullptr;  // [N (x batches), ldw]
+    int M = 0, N = 0, K = 0;
+    int lda = 0, ldw = 0;
+    int w_rows = 0;                    // total rows of W (N, or batches*b_rows_per_batch)
+    Epi epi;
+};
+
+// impl: 0 = tcgen05/TMA (product path), 1 = mma.sync reference kernel (debug / cross-check only)
+int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl = 0);
+int gemm_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes; idempotent
+
+}  // namespace vpu

@@ -1,0 +1,76 @@
+"""Thin torch-tensor wrappers over the kernel-level C-ABI entry points (used by tests and tools).
+Every function launches the hand-written CUDA kernel on the current stream; none has a fallback."""
+import ctypes
+
+import torch
+
+from . import lib as L
+
+_ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2}
+
+
+def _dt(t):
+    return L.VPU_BF16 if t.dtype == torch.bfloat16 else L.VPU_F32
+
+
+def gemm(A, W, bias=None, bias2d=None, residual=None, act=None, out_dtype=torch.bfloat16, impl=0, out=None):
+    """out = act(A @ W.T + bias + bias2d[m % rows] + residual); A [M,K] bf16, W [N,K] bf16."""
+    assert A.is_cuda and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    L.check(L.load().vpu_gemm(L.ptr(A), A.stride(0), L.ptr(W), W.stride(0), M, N, K, L.ptr(bias), L.ptr(bias2d),
+                              0 if bias2d is None else bias2d.shape[0], L.ptr(residual),
+                              0 if residual is None else _dt(residual), 0 if residual is None else residual.stride(0),
+                              _ACT[act], L.ptr(out), _dt(out), out.stride(0), impl, L.current_stream()))
+    return out
+
+
+def gemm_pixel_shuffle(A, W, bias4, g, cout, impl=0):
+    """ConvTranspose2d(k=2,s=2): A [B*g*g, K] bf16, W [4*cout, K] -> NHWC [B, 2g, 2g, cout] bf16."""
+    M, K = A.shape
+    B = M // (g * g)
+    out = torch.empty(B, 2 * g, 2 * g, cout, dtype=torch.bfloat16, device=A.device)
+    L.check(L.load().vpu_gemm_pixel_shuffle(L.ptr(A), L.ptr(W), M, cout, K, L.ptr(bias4), g, L.ptr(out), impl,
+                                            L.current_stream()))
+    return out
+
+
+def attention(q, k, v, Sq, Sk, heads, head_dim, nprob, scale, qoff=0, koff=0, voff=0, window=0, grid=0, out_cols=None):
+    """q/k/v: 2-D bf16 token-major buffers (rows, ld); returns o [rows_q, heads*head_dim] bf16."""
+    cols = out_cols or heads * head_dim
+    o = torch.zeros(q.shape[0], cols, dtype=torch.bfloat16, device=q.device)
+    L.check(L.load().vpu_attention(L.ptr(q), q.stride(0), qoff, L.ptr(k), k.stride(0), koff, L.ptr(v), v.stride(0), voff,
+                                   L.ptr(o), o.stride(0), Sq, Sk, heads, head_dim, nprob, float(scale), window, grid,
+                                   L.current_stream()))
+    return o
+
+
+def layernorm(x, gamma, beta, eps, pe=None, want_rowmax=False):
+    rows, C = x.shape
+    of = torch.empty_like(x)
+    ob = torch.empty(rows, C, dtype=torch.bfloat16, device=x.device)
+    ope = torch.empty(rows, C, dtype=torch.bfloat16, device=x.device) if pe is not None else None
+    rm = torch.empty(rows, dtype=torch.float32, device=x.device) if want_rowmax else None
+    L.check(L.load().vpu_layernorm(L.ptr(x), L.ptr(gamma), L.ptr(beta), float(eps), rows, C, L.ptr(of), L.ptr(ob),
+                                   L.ptr(pe), L.ptr(ope), L.ptr(rm), L.current_stream()))
+    return of, ob, ope, rm
+
+
+def groupnorm_nhwc_(x, gamma, beta, gelu):
+    """In-place GroupNorm(1, C) (+GELU) on NHWC bf16 [B, ..., C]."""
+    B, C = x.shape[0], x.shape[-1]
+    per = x[0].numel()
+    scratch = torch.empty(B * 8200, dtype=torch.uint8, device=x.device)
+    L.check(L.load().vpu_groupnorm_nhwc(L.ptr(x), B, per, C, L.ptr(gamma), L.ptr(beta), int(gelu), L.ptr(scratch),
+                                        L.current_stream()))
+    return x
+
+
+def upsample_align_corners(x, H, W):
+    planes = x.numel() // (x.shape[-1] * x.shape[-2])
+    out = torch.empty(*x.shape[:-2], H, W, dtype=torch.float32, device=x.device)
+    L.check(L.load().vpu_upsample_align_corners(L.ptr(x), L.ptr(out), x.shape[-2], x.shape[-1], H, W, planes,
+                                                L.current_stream()))
+    return out

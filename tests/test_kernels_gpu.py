@@ -1,0 +1,185 @@
+"""GPU: each hand-written kernel, called through the C ABI, against the same op in plain torch fp32
+(floating-point kernels) or the CPU oracle (integer / rasterisation kernels, bit-exact)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand_bf16(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(_dev())
+
+
+GEMM_SHAPES = [
+    # M, N, K            tile config exercised
+    (128, 256, 64),      # one tile, one k-block, BN=256
+    (256, 64, 128),      # BN=64
+    (384, 768, 768),     # BN=256, 12 k-blocks (ring wraps)
+    (1000, 384, 768),    # BN=192, ragged M
+    (3072, 1152, 768),   # BN=192 (DMA image-side projection width)
+    (777, 2304, 768),    # BN=256 ragged M, qkv width
+    (96, 2048, 904),     # PPuE FFN: K=904 (ragged k-block), M < 128
+    (512, 1280, 1176),   # ViT-H patch embed K, BN=256
+    (640, 640, 3072),    # BN=128, long K
+    (20000, 768, 768),   # > 148 tiles: persistent loop + TMEM double buffering
+]
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(M, N, K, impl):
+    from pvpuformer_b200 import ops
+    A, W = _rand_bf16((M, K), 1), _rand_bf16((N, K), 2, 0.05)
+    bias = torch.randn(N, device=_dev())
+    out = ops.gemm(A, W, bias=bias, out_dtype=torch.float32, impl=impl)
+    ref = A.double() @ W.double().t() + bias.double()
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_gemm_epilogues(impl):
+    from pvpuformer_b200 import ops
+    M, N, K = 1568, 768, 256
+    A, W = _rand_bf16((M, K), 3), _rand_bf16((N, K), 4, 0.1)
+    bias = torch.randn(N, device=_dev())
+    tab = torch.randn(784, N, device=_dev())
+    base = A.double() @ W.double().t()
+    # bias2d table (positional tables), fp32 out
+    out = ops.gemm(A, W, bias2d=tab, out_dtype=torch.float32, impl=impl)
+    ref = base + tab.double().repeat(2, 1)
+    assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    # GELU, bf16 out
+    out = ops.gemm(A, W, bias=bias, act="gelu", impl=impl)
+    ref = F.gelu((base + bias.double()).float())
+    assert (out.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    # ReLU
+    out = ops.gemm(A, W, bias=bias, act="relu", impl=impl)
+    ref = F.relu((base + bias.double()).float())
+    assert (out.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    # fp32 residual, in place (the ViT residual stream)
+    x = torch.randn(M, N, device=_dev())
+    ref = x.double() + base + bias.double()
+    out = ops.gemm(A, W, bias=bias, residual=x, out_dtype=torch.float32, impl=impl, out=x)
+    assert out.data_ptr() == x.data_ptr()
+    assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    # bf16 residual, fp32 out (DMA image-side residual)
+    r = _rand_bf16((M, N), 5)
+    out = ops.gemm(A, W, bias=bias, residual=r, out_dtype=torch.float32, impl=impl)
+    ref = r.double() + base + bias.double()
+    assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_gemm_pixel_shuffle_matches_conv_transpose(impl):
+    from pvpuformer_b200 import ops
+    B, g, cin, cout = 2, 28, 256, 192
+    x = _rand_bf16((B, g, g, cin), 6)                       # NHWC
+    w = (torch.randn(cin, cout, 2, 2, generator=torch.Generator().manual_seed(7)) * 0.05).to(_dev())
+    b = torch.randn(cout, device=_dev())
+    wp = w.permute(2, 3, 1, 0).reshape(4 * cout, cin).to(torch.bfloat16).contiguous()
+    out = ops.gemm_pixel_shuffle(x.view(-1, cin), wp, b.repeat(4).contiguous(), g, cout, impl=impl)
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, stride=2).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert (out.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def _attn_ref(q, k, v, scale):
+    a = torch.softmax((q.float() @ k.float().transpose(-1, -2)) * scale, dim=-1)
+    return a @ v.float()
+
+
+@pytest.mark.parametrize("heads,hd,grid,win", [(12, 64, 28, 14), (16, 80, 32, 16)])
+def test_attention_vit_window_and_global(heads, hd, grid, win):
+    from pvpuformer_b200 import ops
+    B, N, C = 2, grid * grid, heads * hd
+    qkv = _rand_bf16((B * N, 3 * C), 8)
+    scale = hd ** -0.5
+    t = qkv.view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)         # [3,B,h,N,d]
+    # global
+    o = ops.attention(qkv, qkv, qkv, N, N, heads, hd, B, scale, 0, C, 2 * C)
+    ref = _attn_ref(t[0], t[1], t[2], scale).transpose(1, 2).reshape(B * N, C)
+    assert (o.float() - ref).abs().max().item() < 2e-2
+    # windowed: reference patchify -> attention per window -> unpatchify (models_vit.py:225-255)
+    nw = grid // win
+
+    def part(x):      # [B,h,N,d] -> [B*nw*nw, h, win*win, d]
+        x = x.reshape(B, heads, nw, win, nw, win, hd).permute(0, 2, 4, 1, 3, 5, 6)
+        return x.reshape(B * nw * nw, heads, win * win, hd)
+    refw = _attn_ref(part(t[0]), part(t[1]), part(t[2]), scale)      # [B*nw2, h, S, d]
+    refw = refw.reshape(B, nw, nw, heads, win, win, hd).permute(0, 1, 4, 2, 5, 3, 6).reshape(B * N, C)
+    o = ops.attention(qkv, qkv, qkv, win * win, win * win, heads, hd, B * nw * nw, scale, 0, C, 2 * C, window=win, grid=grid)
+    assert (o.float() - refw).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("C", [768, 1024, 1280])
+def test_attention_dma_shapes(C):
+    from pvpuformer_b200 import ops
+    B, N, Q, H = 3, 784 if C != 1280 else 1024, 48, 8
+    Ci = C // 2
+    d_self, d_cross = C // H, Ci // H
+    # prompt self-attention 48 x 48
+    qk, v = _rand_bf16((B * Q, 2 * C), 9), _rand_bf16((B * Q, C), 10)
+    o = ops.attention(qk, qk, v, Q, Q, H, d_self, B, 1 / math.sqrt(d_self), 0, C, 0)
+    r = lambda t, n, d: t.reshape(B, n, H, d).transpose(1, 2)
+    ref = _attn_ref(r(qk[:, :C], Q, d_self), r(qk[:, C:], Q, d_self), r(v, Q, d_self), 1 / math.sqrt(d_self))
+    assert (o.float() - ref.transpose(1, 2).reshape(B * Q, C)).abs().max().item() < 2e-2
+    # tokens -> image: 48 queries x N keys, K|V|Q fused buffer of width 3*Ci
+    tq, kvq = _rand_bf16((B * Q, Ci), 11), _rand_bf16((B * N, 3 * Ci), 12)
+    o = ops.attention(tq, kvq, kvq, Q, N, H, d_cross, B, 1 / math.sqrt(d_cross), 0, 0, Ci)
+    ref = _attn_ref(r(tq, Q, d_cross), r(kvq[:, :Ci], N, d_cross), r(kvq[:, Ci:2 * Ci], N, d_cross), 1 / math.sqrt(d_cross))
+    assert (o.float() - ref.transpose(1, 2).reshape(B * Q, Ci)).abs().max().item() < 2e-2
+    # image -> tokens: N queries x 48 keys
+    ik, iv = _rand_bf16((B * Q, Ci), 13), _rand_bf16((B * Q, Ci), 14)
+    o = ops.attention(kvq, ik, iv, N, Q, H, d_cross, B, 1 / math.sqrt(d_cross), 2 * Ci, 0, 0, out_cols=Ci)
+    ref = _attn_ref(r(kvq[:, 2 * Ci:], N, d_cross), r(ik, Q, d_cross), r(iv, Q, d_cross), 1 / math.sqrt(d_cross))
+    assert (o.float() - ref.transpose(1, 2).reshape(B * N, Ci)).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("C", [768, 1024, 1280])
+def test_layernorm(C):
+    from pvpuformer_b200 import ops
+    rows = 1003
+    x = torch.randn(rows, C, device=_dev()) * 3 + 0.5
+    g, b, pe = torch.randn(C, device=_dev()), torch.randn(C, device=_dev()), torch.randn(rows, C, device=_dev())
+    of, ob, ope, rm = ops.layernorm(x, g, b, 1e-6, pe=pe, want_rowmax=True)
+    ref = F.layer_norm(x, (C,), g, b, 1e-6)
+    assert (of - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(ob, of.to(torch.bfloat16))
+    assert (ope.float() - (ref + pe)).abs().max().item() < 1e-2 * (ref + pe).abs().max().item()
+    assert (rm - ref.max(dim=1).values).abs().max().item() < 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("gelu", [0, 1])
+def test_groupnorm_nhwc(gelu):
+    from pvpuformer_b200 import ops
+    B, H, C = 3, 56, 384
+    x = _rand_bf16((B, H, H, C), 15, 2.0) + 0.25
+    g, b = torch.randn(C, device=_dev()), torch.randn(C, device=_dev())
+    ref = F.group_norm(x.float().permute(0, 3, 1, 2), 1, g, b, 1e-5)
+    if gelu:
+        ref = F.gelu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    out = ops.groupnorm_nhwc_(x.clone(), g, b, gelu)
+    assert (out.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_upsample_align_corners():
+    from pvpuformer_b200 import ops
+    x = torch.randn(2, 5, 112, 112, device=_dev())
+    out = ops.upsample_align_corners(x, 448, 448)
+    ref = F.interpolate(x, size=(448, 448), mode="bilinear", align_corners=True)
+    assert (out - ref).abs().max().item() < 1e-5
+    x = torch.randn(1, 3, 128, 128, device=_dev())
+    out = ops.upsample_align_corners(x, 448, 448)
+    ref = F.interpolate(x, size=(448, 448), mode="bilinear", align_corners=True)
+    assert (out - ref).abs().max().item() < 1e-5
