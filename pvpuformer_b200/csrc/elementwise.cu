@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
         auto st = [&](__nv_bfloat16* dst, size_t off, const float4& v) {
             *reinterpret_cast<uint2*>(dst + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
         };
-        st(a.x0, (size_t)m * a.C + c, x);
+        if (a.x0) st(a.x0, (size_t)m * a.C + c, x);
         st(a.x2, (size_t)m * a.C + c, gate(0));
         st(a.x3, (size_t)m * a.C + c, gate(1));
         const int i = tok / g, j = tok % g;
