@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the per-click VPUFormer forward (BASELINE.json metric: click-forwards/s, ViT-B/448).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+One step = one pass of the hot path (forward(image, points) -> instances + instances_aux) over one batch
+of synthetic input: BASELINE.json configs[1], ViT-B/448 batch 64 per GPU (weak scaling: every rank runs
+its own 64 click-forwards; no collective in the forward).  Prints ONE JSON line on rank 0.
+
+  value        click-forwards/s, inputs resident in HBM, CUDA events over exactly K steps, max over ranks
+  e2e          same metric through the public module call with HOST (pinned) inputs: H2D of the image and
+               click tensors and D2H of `instances` inside the timed region, every step
+  roofline     tcgen05 GEMM kernel class: algorithmic FLOPs / CUDA-event time of its launches (events
+               recorded by the C ABI around every launch on the launching stream), vs MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (port of the reference forward) on this host's cores, bounded sample
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "click-forwards/sec"
+GFLOP_PER_CLICK_FORWARD = {"vit_base": 170.7, "vit_large": 538.7, "vit_huge": 1422.8}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="vit_base", choices=["vit_base", "vit_large", "vit_huge"])
+    ap.add_argument("--batch", type=int, default=64, help="click-forwards per step per GPU")
+    ap.add_argument("--no-aux", action="store_true", help="skip the 48-channel aux output (NoBRS only reads instances)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--ref-batch", type=int, default=8, help="click-forwards per CPU step (--impl reference)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+def workload(arch, batch, seed):
+    from pvpuformer_b200 import synthetic
+    image4 = synthetic.images(batch, seed=seed)
+    points = synthetic.random_clicks(batch, seed=seed + 1, dtype=torch_mod().float64)
+    return image4, points
+
+
+def torch_mod():
+    import torch
+    return torch
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own algorithm for the path, restated in oracle/vpu_oracle.py (the Python
+# reference tree itself does not travel to the GPU box).  Times whole forwards on the host cores.
+# ---------------------------------------------------------------------------------------------
+def cpu_forward_rate(arch, batch, steps, warmup, budget_s=None):
+    import torch
+    from oracle import vpu_oracle as vo
+    from pvpuformer_b200.config import make_config
+    from pvpuformer_b200.weights import synthetic_state_dict
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    cfg = make_config(arch)
+    sd = synthetic_state_dict(cfg, 0)
+    image4, points = workload(arch, batch, seed=11)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            vo.forward(sd, cfg, image4, points)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if budget_s is not None and i >= warmup and sum(times) > budget_s:
+                break
+    total = sum(times)
+    return {"value": batch * len(times) / total, "unit": METRIC, "cores": cores, "kind": "port",
+            "sample": "%d steps x %d click-forwards of the same synthetic %s workload, fp32, %d torch threads"
+                      % (len(times), batch, arch, cores)}, total / len(times), len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cb, step_s, nsteps = cpu_forward_rate(args.arch, args.ref_batch, args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus,
+            "steps": nsteps, "warmup": min(args.warmup, 1), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "VPUFormer %s 448 per-click forward; CPU step = %d click-forwards" % (args.arch, args.ref_batch),
+                       "arch": args.arch, "batch_per_step": args.ref_batch},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def profile_classes(model, L, steps, run_step):
+    import torch
+    lib = L.load()
+    L.check(lib.vpu_profile_begin(model._handle))
+    for _ in range(steps):
+        run_step()
+    torch.cuda.synchronize()
+    arr = (L.VpuProfileEntry * 64)()
+    n = ctypes.c_int(0)
+    L.check(lib.vpu_profile_end(model._handle, arr, 64, ctypes.byref(n)))
+    out = []
+    for i in range(n.value):
+        e = arr[i]
+        out.append({"name": e.name.decode(), "ms": e.ms / steps, "flops": e.flops / steps, "bytes": e.bytes / steps,
+                    "launches": e.launches // steps})
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    from pvpuformer_b200 import lib as L
+    from pvpuformer_b200.config import make_config
+    from pvpuformer_b200.model import build_model
+    from pvpuformer_b200.weights import synthetic_state_dict
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = make_config(args.arch)
+    model = build_model(args.arch, state_dict=synthetic_state_dict(cfg, 0), device=dev)
+    model.want_aux = not args.no_aux
+    B = args.batch
+    image_h, points_h = workload(args.arch, B, seed=100 + rank)       # every rank: its own click sessions
+    image_h, points_h = image_h.pin_memory(), points_h.pin_memory()
+    image_d, points_d = image_h.to(dev), points_h.to(dev)
+    lib = L.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return model(image_d, points_d)
+
+    out_h = torch.empty(B, 1, cfg.img_size, cfg.img_size, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        img = image_h.to(dev, non_blocking=True)
+        pts = points_h.to(dev, non_blocking=True)
+        o = model(img, pts)
+        out_h.copy_(o["instances"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the result of every step
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        l0 = lib.vpu_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        launches = lib.vpu_launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, clocks
+
+    ms, launches, clocks = timed(step_resident, args.steps, max(args.warmup, 3), sample_clocks=True)
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        ms_e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+        e2e = {"value": world * B * args.steps / (ms_e * 1e-3), "unit": METRIC,
+               "h2d_bytes_per_step": image_h.numel() * 4 + points_h.numel() * 8, "d2h_bytes_per_step": out_h.numel() * 4,
+               "ms_per_step": ms_e / args.steps,
+               "call": "VitMultiGaussianVector_ed_Model.forward(image, points) with pinned host tensors; D2H of 'instances'"}
+
+    classes = profile_classes(model, L, args.profile_steps, step_resident) if rank == 0 else []
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    gemm = [c for c in classes if c["name"].startswith("gemm.")]
+    attn = [c for c in classes if c["name"].startswith("attn.")]
+    tot_ms = sum(c["ms"] for c in classes) or 1.0
+
+    def tf(cs):
+        t = sum(c["ms"] for c in cs)
+        return (sum(c["flops"] for c in cs) / (t * 1e-3) / 1e12) if t > 0 else 0.0
+
+    g_tf = tf(gemm)
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN> (tcgen05.mma + TMA, all GEMMs of the forward)",
+                "achieved": g_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": g_tf / pk["tf_sustained"],
+                "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["src"],
+                "share_of_step": sum(c["ms"] for c in gemm) / tot_ms,
+                "launches_per_step": sum(c["launches"] for c in gemm), "traffic": None}
+    attn_info = {}
+    for c in attn:
+        attn_info[c["name"]] = {"ms_per_step": c["ms"], "tflops": tf([c]), "frac_of_tensor_peak": tf([c]) / pk["tf_sustained"],
+                                "launches": c["launches"]}
+    kernels = [{"name": c["name"], "ms_per_step": round(c["ms"], 4), "share": round(c["ms"] / tot_ms, 4),
+                "tflops": round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 1) if c["flops"] and c["ms"] > 0 else None,
+                "gbs": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1) if c["ms"] > 0 else None, "launches": c["launches"]}
+               for c in sorted(classes, key=lambda c: -c["ms"])]
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _, _ = cpu_forward_rate(args.arch, args.ref_batch, 3, 1, budget_s=25.0)
+
+    step_tflops = world * B * GFLOP_PER_CLICK_FORWARD[args.arch] * 1e9 * args.steps / (ms * 1e-3) / 1e12
+    line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "VPUFormer %s 448 batched per-click forward, batch %d synthetic images per GPU "
+                                   "(BASELINE.json configs[1]); random-init weights; outputs instances%s" %
+                                   (args.arch, B, "" if args.no_aux else " + instances_aux"),
+                       "arch": args.arch, "batch_per_gpu": B, "clicks": "1..20 per image", "parallelism": "dp%d (independent click sessions, no collective)" % world,
+                       "l2": "inputs + workspace per step (>4 GB) exceed the 126 MB L2; no explicit flush"},
+            "step_tflops_algorithmic": step_tflops, "step_frac_of_tensor_peak": step_tflops / world / pk["tf_sustained"],
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "attention": attn_info,
+            "kernels": kernels, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,8 @@ enum { VPU_F32 = 0, VPU_BF16 = 1, VPU_I32 = 2, VPU_F64 = 3, VPU_U8 = 4 };
 
 const char* vpu_last_error(void);
 int vpu_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py "gpu_launches"). */
+unsigned long long vpu_launch_count(void);
 
 /* ---- lifecycle (replaces VitMultiGaussianVector_ed_Model.__init__ / load_state_dict,
  *      reference is_vpu_model.py:142-186, inference/utils.py:21-46) ---- */
@@ -83,6 +85,20 @@ typedef struct vpu_prompts {
 int vpu_forward(vpu_handle h, const float* image4 /* [B,4,img,img] fp32 */, const vpu_prompts* prompts, int B,
                 float* instances /* [B,1,img,img] */, float* instances_aux /* [B,48,img,img] or NULL */,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- per-kernel-class device timing (bench.py roofline; measurement only) ----
+ * Between vpu_profile_begin and vpu_profile_end every launch of vpu_forward is bracketed by CUDA events on the
+ * caller's stream.  vpu_profile_end waits for the last event and returns one entry per kernel class
+ * ("gemm.vit_window", "attn.dma", "ln.vit_global", ...): summed device ms, algorithmic FLOPs / bytes, launches. */
+typedef struct vpu_profile_entry {
+    char name[48];
+    double ms;
+    double flops;
+    double bytes;
+    int64_t launches;
+} vpu_profile_entry;
+int vpu_profile_begin(vpu_handle h);
+int vpu_profile_end(vpu_handle h, vpu_profile_entry* out, int max_entries, int* n_out);
 
 /* ---- stage entry points (also what the parity tests call) ---- */
 /* PPuE rows (reference is_vpu_model.py:189-352, ops.py:39-325) -> out [B, 2*num_max_points, 2*img+3] fp32 */

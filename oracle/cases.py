@@ -9,14 +9,7 @@ import numpy as np
 import torch
 
 
-def images(B, seed, prev="sigmoid", size=448):
-    g = torch.Generator().manual_seed(seed)
-    img = torch.rand(B, 3, size, size, generator=g)
-    if prev == "sigmoid":
-        pm = torch.sigmoid(torch.randn(B, 1, size, size, generator=g))
-    else:
-        pm = torch.zeros(B, 1, size, size)
-    return torch.cat([img, pm], 1)
+from pvpuformer_b200.synthetic import images, random_clicks  # noqa: F401  (one definition, shared with bench.py)
 
 
 # clicks exercising: centre, fractional coords, corner drop quirk (5,440), image corner, (0,0),
@@ -25,27 +18,6 @@ CLICKS_A = torch.tensor(
     [[[224., 224, 0], [100, 50.5, 2], [-1, -1, -1], [300, 310, 1], [-1, -1, -1], [-1, -1, -1]],
      [[5, 440, 0], [-1, -1, -1], [-1, -1, -1], [447, 447, 1], [0, 0, 2], [200.7, 13.2, 3]]],
     dtype=torch.float64)
-
-
-def random_clicks(B, seed, max_clicks=20, size=448, dtype=torch.float32):
-    """per image k in U{1..max} clicks, first positive, others +-, packed by
-    the get_points_nd rule (reference isegm/inference/predictors/base.py:195-213)."""
-    rs = np.random.RandomState(seed)
-    per = []
-    for b in range(B):
-        k = rs.randint(1, max_clicks + 1)
-        pos, neg = [], []
-        for i in range(k):
-            rc = (float(rs.randint(0, size)), float(rs.randint(0, size)), float(i))
-            (pos if (i == 0 or rs.rand() < 0.5) else neg).append(rc)
-        per.append((pos, neg))
-    n = max(1, max(max(len(p), len(q)) for p, q in per))
-    out = []
-    for pos, neg in per:
-        pos = pos + [(-1., -1., -1.)] * (n - len(pos))
-        neg = neg + [(-1., -1., -1.)] * (n - len(neg))
-        out.append(pos + neg)
-    return torch.tensor(out, dtype=dtype)
 
 
 def ellipse_masks(B, seed, size=448):

@@ -45,6 +45,32 @@ struct Plan {
     }
 };
 
+// Optional per-kernel-class device timing (bench.py roofline): CUDA events recorded on the caller's
+// stream around every launch of vpu_forward.  Off by default; event creation happens only here.
+struct ProfRec {
+    std::string cls;
+    double flops, bytes;
+    int launches;
+    cudaEvent_t e0, e1;
+};
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    ~Profiler() {
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+};
+
 }  // namespace vpu
 
 using namespace vpu;
@@ -57,12 +83,14 @@ struct vpu_context {
     int gemm_impl = 0;
     float click_table[32];
     int click_radius = 9;
+    Profiler prof;
 
     int C() const { return d.embed_dim; }
     int grid() const { return d.img_size / d.patch; }
     int N() const { return grid() * grid(); }
     int Q() const { return 2 * d.num_max_points; }
-    int K0() const { return 6 * d.patch * d.patch; }
+    int K0() const { return 6 * d.patch * d.patch; }    // fused (image | coords) patch-embed K
+    int K0s() const { return 10 * d.patch * d.patch; }  // + split-bf16 residual planes of image and prev mask
     int ppue_dim() const { return 2 * d.img_size + 3; }
     int ppue_ld() const { return (ppue_dim() + 7) / 8 * 8; }
     int d4() const { return std::max(d.out_dims[0] * 2, d.embed_dim / 2); }
@@ -79,7 +107,7 @@ Plan make_plan(const vpu_context& h, int B) {
     const size_t g2 = 2 * g, g4 = 4 * g, gh = g / 2, hc = h.d.head_channels;
     p.add("ppue", (size_t)B * Q * h.ppue_dim() * 4);
     p.add("ppue_b", MQ * h.ppue_ld() * 2);
-    p.add("A0", M * h.K0() * 2);
+    p.add("A0", M * h.K0s() * 2);
     p.add("X", M * C * 4);
     p.add("Xn", M * C * 2);
     p.add("QKV", M * 3 * C * 2);
@@ -151,6 +179,23 @@ struct Fwd {
     uint8_t* ws;
     Plan plan;
     int B;
+    const char* stage = "";
+
+    // run one launch helper; in profiling mode bracket it with events and book flops / algorithmic bytes
+    template <typename F> int timed(const char* kind, double flops, double bytes, F&& fn) {
+        if (!h.prof.on) return fn();
+        ProfRec r;
+        r.cls = std::string(kind) + "." + stage;
+        r.flops = flops; r.bytes = bytes;
+        r.e0 = h.prof.get(); r.e1 = h.prof.get();
+        const unsigned long long l0 = launch_count();
+        cudaEventRecord(r.e0, s);
+        const int rc = fn();
+        cudaEventRecord(r.e1, s);
+        r.launches = (int)(launch_count() - l0);
+        h.prof.recs.push_back(r);
+        return rc;
+    }
 
     template <typename T> T* buf(const char* name) { return reinterpret_cast<T*>(ws + plan.find(name)->off); }
     template <typename T> const T* W(const std::string& key) { return reinterpret_cast<const T*>(h.w.at(key).p); }
@@ -167,7 +212,8 @@ struct Fwd {
         p.w_rows = Nn;
         p.epi.out = out; p.epi.out_bf16 = out_bf16; p.epi.ldo = ldo; p.epi.bias = bias; p.epi.act = act;
         p.epi.res = res; p.epi.res_bf16 = res_bf16; p.epi.ldr = ldr; p.epi.bias2d = tab; p.epi.bias2d_rows = tab_rows;
-        return gemm_launch(p, s, h.gemm_impl);
+        const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0));
+        return timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
     }
     int gemm_ps(const __nv_bfloat16* A, const std::string& wkey, const float* bias4, int M, int cout, int K, int g,
                 __nv_bfloat16* out) {
@@ -175,18 +221,22 @@ struct Fwd {
         p.A = A; p.W = Wb(wkey); p.M = M; p.N = 4 * cout; p.K = K; p.lda = K; p.ldw = K; p.w_rows = 4 * cout;
         p.epi.out = out; p.epi.out_bf16 = 1; p.epi.ldo = cout; p.epi.bias = bias4; p.epi.mode = EPI_PIXEL_SHUFFLE;
         p.epi.ps_g = g; p.epi.ps_cout = cout;
-        return gemm_launch(p, s, h.gemm_impl);
+        const double by = 2.0 * ((double)M * K + 4.0 * cout * K + 4.0 * M * cout);
+        return timed("gemm", 8.0 * M * cout * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
     }
     int ln(const float* in, const std::string& key, float eps, int rows, float* of, __nv_bfloat16* ob,
            const float* pe = nullptr, __nv_bfloat16* ope = nullptr, float* rowmax = nullptr) {
         LnArgs a;
         a.in = in; a.gamma = Wf(key + ".g"); a.beta = Wf(key + ".b"); a.eps = eps; a.rows = rows;
         a.out_f32 = of; a.out_bf16 = ob; a.pe = pe; a.out_pe_bf16 = ope; a.rowmax = rowmax;
-        return layernorm_launch(a, h.C(), s);
+        const double by = (double)rows * h.C() * (4 + (of ? 4 : 0) + (ob ? 2 : 0) + (ope ? 6 : 0));
+        return timed("ln", 0, by, [&] { return layernorm_launch(a, h.C(), s); });
     }
     int gn(__nv_bfloat16* x, size_t per_sample, int Cc, const std::string& key, int gelu) {
-        return groupnorm_launch(x, B, per_sample, Cc, Wf(key + ".g"), Wf(key + ".b"), gelu, buf<float2>("gn_partial"),
-                                buf<float2>("gn_stats"), s);
+        return timed("gn", 0, 6.0 * B * (double)per_sample, [&] {
+            return groupnorm_launch(x, B, per_sample, Cc, Wf(key + ".g"), Wf(key + ".b"), gelu, buf<float2>("gn_partial"),
+                                    buf<float2>("gn_stats"), s);
+        });
     }
     int attn(const __nv_bfloat16* q, int ldq, int qoff, const __nv_bfloat16* k, int ldk, int koff, const __nv_bfloat16* v,
              int ldv, int voff, __nv_bfloat16* o, int ldo, int Sq, int Sk, int heads, int hd, int nprob, float scale,
@@ -202,7 +252,9 @@ struct Fwd {
             a.qmap.mode = 0; a.qmap.per_prob = Sq;
             a.kmap.mode = 0; a.kmap.per_prob = Sk;
         }
-        return attention_launch(a, hd, s);
+        const double fl = 4.0 * Sq * Sk * hd * heads * nprob;
+        const double by = 2.0 * hd * heads * nprob * (2.0 * Sq + 2.0 * Sk);
+        return timed("attn", fl, by, [&] { return attention_launch(a, hd, s); });
     }
 };
 
@@ -237,10 +289,16 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     CoordArgs ca;
     ca.image4 = image4; ca.points = pr.points; ca.extra_mask = pr.extra_mask; ca.n = pr.n; ca.H = img; ca.W = img;
     ca.radius = h.d.norm_radius;
-    RUN(patch_operand_launch(ca, B, f.buf<bf>("A0"), h.d.patch, h.K0(), s));
+    f.stage = "patch_embed";
+    RUN(f.timed("patch_operand", 0, (double)B * img * img * (16.0 + 20.0), [&] {
+        return patch_operand_launch(ca, B, f.buf<bf>("A0"), h.d.patch, h.K0s(), s);
+    }));
+    // 3-term split-bf16 product (A_hi + A_lo)(W_hi + W_lo) ~ A_hi W_hi + A_lo W_hi + A_hi W_lo: the token
+    // embedding feeds the fp32 residual stream of every block, so it is computed to ~fp32 accuracy.
     float* X = f.buf<float>("X");
-    RUN(f.gemm(f.buf<bf>("A0"), h.K0(), "pe.w", M, C, h.K0(), nullptr, X, false, C, ACT_NONE, nullptr, false, 0,
+    RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w", M, C, h.K0s(), nullptr, X, false, C, ACT_NONE, nullptr, false, 0,
                f.Wf("pe.tab"), N));
+    RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w_lo", M, C, h.K0(), nullptr, X, false, C, ACT_NONE, X, false, C));
 
     // ---- A8-A9: ViT blocks ----
     bf* Xn = f.buf<bf>("Xn");
@@ -254,6 +312,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     for (int i = 1; i <= h.d.depth; ++i) {
         const std::string k = "blk" + std::to_string(i - 1);
         const bool windowed = (i % h.group()) != 0;
+        f.stage = windowed ? "vit_window" : "vit_global";
         RUN(f.ln(X, k + ".ln1", 1e-6f, M, nullptr, Xn));
         RUN(f.gemm(Xn, C, k + ".qkv.w", M, 3 * C, C, f.Wf(k + ".qkv.b"), QKV, true, 3 * C));
         if (windowed)
@@ -275,7 +334,8 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     pa.out = f.buf<float>("ppue");
     pa.out_bf16 = f.buf<bf>("ppue_b");
     pa.ld_bf16 = h.ppue_ld();
-    RUN(ppue_launch(pa, B, s));
+    f.stage = "ppue";
+    RUN(f.timed("ppue", 0, (double)MQ * (h.ppue_dim() * 4.0 + h.ppue_ld() * 2.0), [&] { return ppue_launch(pa, B, s); }));
     float* Q0 = f.buf<float>("Q0");
     RUN(f.gemm(f.buf<bf>("ppue_b"), h.ppue_ld(), "ffn.w1", MQ, h.d.ppue_ffn_dim, h.ppue_ld(), f.Wf("ffn.b1"), f.buf<bf>("T1"),
                true, h.d.ppue_ffn_dim, ACT_RELU));
@@ -291,8 +351,9 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     bf* Kb = f.buf<bf>("Kb");
     bf* KVQ = f.buf<bf>("KVQ");
     float* rowmax = f.buf<float>("rowmax");
-    RUN(cast_add_launch(Q0, nullptr, Q0b, (size_t)MQ * C, s));
-    RUN(cast_add_launch(X, nullptr, X0b, (size_t)M * C, s));
+    f.stage = "dma";
+    RUN(f.timed("cast", 0, 6.0 * MQ * C, [&] { return cast_add_launch(Q0, nullptr, Q0b, (size_t)MQ * C, s); }));
+    RUN(f.timed("cast", 0, 6.0 * M * C, [&] { return cast_add_launch(X, nullptr, X0b, (size_t)M * C, s); }));
     const int dh = h.d.dma_heads, Ci = C / 2, dself = C / dh, dcross = Ci / dh;
     const float* Qf = Q0;  // current fp32 queries
     const bf* Kin = X0b;   // current bf16 keys
@@ -346,14 +407,18 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     RUN(f.ln(T, "dmaf.n", 1e-5f, MQ, f.buf<float>("qfin"), nullptr));
 
     // ---- A14: merge ----
-    RUN(qout_gate_launch(Q0, ql[0], ql[1], f.buf<float>("qfin"), B, Q, C, f.buf<float>("qout"), f.buf<bf>("qout_b"),
-                         f.buf<float>("cg"), s));
+    f.stage = "merge";
+    RUN(f.timed("qout_gate", 0, 22.0 * MQ * C, [&] {
+        return qout_gate_launch(Q0, ql[0], ql[1], f.buf<float>("qfin"), B, Q, C, f.buf<float>("qout"), f.buf<bf>("qout_b"),
+                                f.buf<float>("cg"), s);
+    }));
     MergeArgs ma;
     ma.x = X; ma.cg = f.buf<float>("cg"); ma.rowmax = rowmax; ma.x2 = f.buf<bf>("x2"); ma.x3 = f.buf<bf>("x3");
     ma.x4_s2d = f.buf<bf>("x4"); ma.B = B; ma.N = N; ma.M = M; ma.C = C; ma.grid = g;
-    RUN(merge_launch(ma, s));
+    RUN(f.timed("merge", 0, 10.0 * M * C, [&] { return merge_launch(ma, s); }));
 
     // ---- A15: 4-scale pyramid (NHWC bf16; ConvT/Conv with stride == kernel are plain GEMMs) ----
+    f.stage = "neck";
     const int d4 = h.d4(), d8 = h.d8(), d32 = h.d32();
     const int* od = h.d.out_dims;
     const size_t g2 = 2 * g, g4 = 4 * g, gh = g / 2;
@@ -378,6 +443,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     RUN(f.gn(f.buf<bf>("P32"), gh * gh * od[3], od[3], "d32.gn2", 1));
 
     // ---- A16: head ----
+    f.stage = "head";
     const int hc = h.d.head_channels;
     const char* pyr[4] = {"P4", "P8", "P16", "P32"};
     const size_t res[4] = {g4, g2, (size_t)g, gh};
@@ -393,10 +459,10 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         hca.res[i] = (int)res[i];
     }
     hca.bias = f.Wf("hd.f.b"); hca.out = f.buf<bf>("F"); hca.rnorm = f.buf<float>("rnorm"); hca.B = B;
-    RUN(head_combine_launch(hca, s));
+    RUN(f.timed("head_combine", 0, (double)B * hc * 2.0 * (2.0 * g4 * g4 + g2 * g2 + (double)g * g + gh * gh), [&] { return head_combine_launch(hca, s); }));
     RUN(f.gemm(f.buf<bf>("qout_b"), C, "hd.q.w1", MQ, 2 * C, C, f.Wf("hd.q.b1"), f.buf<bf>("QF"), true, 2 * C, ACT_RELU));
     RUN(f.gemm(f.buf<bf>("QF"), 2 * C, "hd.q.w2", MQ, hc, 2 * C, f.Wf("hd.q.b2"), f.buf<float>("QE"), false, hc));
-    RUN(head_queries_launch(f.buf<float>("QE"), f.Wf("hd.seg.w"), B, Q, f.buf<bf>("QN"), s));
+    RUN(f.timed("head_queries", 0, (double)B * 64 * hc * 6.0, [&] { return head_queries_launch(f.buf<float>("QE"), f.Wf("hd.seg.w"), B, Q, f.buf<bf>("QN"), s); }));
     {
         GemmProblem p;
         p.A = f.buf<bf>("F"); p.W = f.buf<bf>("QN"); p.M = (int)(B * g4 * g4); p.N = 64; p.K = hc; p.lda = hc; p.ldw = hc;
@@ -404,11 +470,18 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         p.epi.mode = EPI_HEAD_FINAL; p.epi.m_per_batch = (int)(g4 * g4); p.epi.b_rows_per_batch = 64;
         p.epi.rnorm = f.buf<float>("rnorm"); p.epi.aux_out = aux ? f.buf<float>("aux_low") : nullptr;
         p.epi.seg_out = f.buf<float>("seg_low"); p.epi.seg_bias = h.scalars.at("hd.seg.b"); p.epi.nq = Q;
-        RUN(gemm_launch(p, s, h.gemm_impl));
+        const double by = (double)p.M * (hc * 2.0 + 4.0 + (aux ? Q * 4.0 : 0.0) + 4.0);
+        RUN(f.timed("gemm", 2.0 * p.M * 64.0 * hc, by, [&] { return gemm_launch(p, s, h.gemm_impl); }));
     }
     // ---- A17: final upsampling (align_corners=True) ----
-    RUN(upsample_ac_launch(f.buf<float>("seg_low"), instances, (int)g4, (int)g4, img, img, (size_t)B, s));
-    if (aux) RUN(upsample_ac_launch(f.buf<float>("aux_low"), aux, (int)g4, (int)g4, img, img, (size_t)B * Q, s));
+    f.stage = "final";
+    RUN(f.timed("upsample_seg", 0, 4.0 * B * ((double)g4 * g4 + (double)img * img), [&] {
+        return upsample_ac_launch(f.buf<float>("seg_low"), instances, (int)g4, (int)g4, img, img, (size_t)B, s);
+    }));
+    if (aux)
+        RUN(f.timed("upsample_aux", 0, 4.0 * B * Q * ((double)g4 * g4 + (double)img * img), [&] {
+            return upsample_ac_launch(f.buf<float>("aux_low"), aux, (int)g4, (int)g4, img, img, (size_t)B * Q, s);
+        }));
     return 0;
 }
 
@@ -433,7 +506,8 @@ std::vector<Need> needed_weights(const vpu_context& h) {
         v.push_back({k + ".g", VPU_F32, {c}});
         v.push_back({k + ".b", VPU_F32, {c}});
     };
-    v.push_back({"pe.w", VPU_BF16, {C, h.K0()}});
+    v.push_back({"pe.w", VPU_BF16, {C, h.K0s()}});
+    v.push_back({"pe.w_lo", VPU_BF16, {C, h.K0()}});
     v.push_back({"pe.tab", VPU_F32, {N, C}});
     for (int i = 0; i < h.d.depth; ++i) {
         const std::string k = "blk" + std::to_string(i);
@@ -486,6 +560,46 @@ extern "C" {
 
 const char* vpu_last_error(void) { return vpu::last_error(); }
 int vpu_version(void) { return 1; }
+unsigned long long vpu_launch_count(void) { return vpu::launch_count(); }
+
+int vpu_profile_begin(vpu_handle h) {
+    if (!valid_handle(h)) return 1;
+    h->prof.on = true;
+    h->prof.recs.clear();
+    h->prof.used = 0;
+    return 0;
+}
+
+int vpu_profile_end(vpu_handle h, vpu_profile_entry* out, int max_entries, int* n_out) {
+    if (!valid_handle(h)) return 1;
+    VPU_REQUIRE(out && n_out && max_entries > 0, "vpu_profile_end: bad argument");
+    h->prof.on = false;
+    std::vector<std::string> order;
+    std::unordered_map<std::string, vpu_profile_entry> agg;
+    if (!h->prof.recs.empty()) VPU_CHECK_CUDA(cudaEventSynchronize(h->prof.recs.back().e1));
+    for (const ProfRec& r : h->prof.recs) {
+        float ms = 0.f;
+        VPU_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        auto it = agg.find(r.cls);
+        if (it == agg.end()) {
+            vpu_profile_entry e;
+            memset(&e, 0, sizeof(e));
+            strncpy(e.name, r.cls.c_str(), sizeof(e.name) - 1);
+            it = agg.emplace(r.cls, e).first;
+            order.push_back(r.cls);
+        }
+        it->second.ms += ms; it->second.flops += r.flops; it->second.bytes += r.bytes; it->second.launches += r.launches;
+    }
+    int n = 0;
+    for (const std::string& k : order) {
+        if (n == max_entries) break;
+        out[n++] = agg[k];
+    }
+    *n_out = n;
+    h->prof.recs.clear();
+    h->prof.used = 0;
+    return 0;
+}
 
 int vpu_create(vpu_handle* out, const vpu_dims* dims) {
     VPU_REQUIRE(out && dims, "vpu_create: null argument");

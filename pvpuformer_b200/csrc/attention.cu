@@ -219,6 +219,7 @@ static int launch_att(const AttnArgs& a, cudaStream_t stream) {
     dim3 grid((a.Sq + ATT_BM - 1) / ATT_BM, a.heads, a.nprob);
     attention_kernel<D><<<grid, ATT_THREADS, smem, stream>>>(a);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

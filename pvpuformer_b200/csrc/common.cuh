@@ -10,6 +10,8 @@ namespace vpu {
 
 // ---- host-side error plumbing (thread-local message read back by vpu_last_error) -----------
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);        // every kernel launch of this library is counted (vpu_launch_count)
+unsigned long long launch_count();
 #define VPU_CHECK_CUDA(expr)                                                              \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

@@ -70,6 +70,7 @@ int layernorm_launch(const LnArgs& a, int C, cudaStream_t stream) {
         default: VPU_REQUIRE(false, "layernorm: unsupported width %d (768/1024/1280)", C);
     }
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -92,6 +93,7 @@ int cast_add_launch(const float* a, const float* b, __nv_bfloat16* out, size_t n
     if (grid > 148 * 16) grid = 148 * 16;
     cast_add_kernel<<<grid, 256, 0, stream>>>(a, b, out, n4);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -171,6 +173,7 @@ int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const fl
     gn_finalize_kernel<<<B, 32, 0, stream>>>(partial, chunks, (double)per_sample, 1e-5f, mean_rstd);
     gn_apply_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, per_sample, C, mean_rstd, gamma, beta, gelu);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch(3);
     return 0;
 }
 
@@ -201,6 +204,7 @@ int qout_gate_launch(const float* q0, const float* q1, const float* q2, const fl
                      __nv_bfloat16* qout_bf16, float* cg, cudaStream_t stream) {
     qout_gate_kernel<<<dim3((C + 127) / 128, B), 128, 0, stream>>>(q0, q1, q2, q3, T, C, qout, qout_bf16, cg);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -241,6 +245,7 @@ int merge_launch(const MergeArgs& a, cudaStream_t stream) {
     if (grid > 148 * 16) grid = 148 * 16;
     merge_kernel<<<grid, 256, 0, stream>>>(a);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -305,6 +310,7 @@ int head_combine_launch(const HeadCombineArgs& a, cudaStream_t stream) {
     const size_t npix = (size_t)a.B * a.res[0] * a.res[0];
     head_combine_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, stream>>>(a);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -333,6 +339,7 @@ int head_queries_launch(const float* qe, const float* wseg, int B, int nq, __nv_
     VPU_REQUIRE(nq < 64, "head queries: nq must be < 64");
     head_queries_kernel<<<dim3(B, 64), 256, 0, stream>>>(qe, wseg, nq, out);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -374,6 +381,7 @@ int upsample_ac_launch(const float* in, float* out, int h, int w, int H, int W, 
     if (grid > 148 * 32) grid = 148 * 32;
     upsample_ac_kernel<<<(unsigned)grid, 256, 0, stream>>>(in, out, h, w, H, W, planes);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

@@ -10,6 +10,7 @@
 //
 // CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..9 epilogue
 // (two warps per TMEM lane quarter, each taking half of the tile's columns).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -27,6 +28,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------
 // Epilogue: CNT consecutive columns [n0, n0+CNT) of output row m.
@@ -424,6 +429,7 @@ static int launch_tc(const GemmProblem& p, cudaStream_t stream) {
     GemmDims d{p.M, p.N, p.K};
     gemm_tc_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d, p.epi);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -444,6 +450,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         if (p.epi.m_per_batch > 0) VPU_REQUIRE(p.epi.m_per_batch % 64 == 0, "m_per_batch must be a multiple of 64");
         gemm_mma_kernel<<<grid, 128, 0, stream>>>(p.A, p.W, p.lda, p.ldw, d, p.epi);
         VPU_CHECK_CUDA(cudaGetLastError());
+        count_launch();
         return 0;
     }
     if (p.N % 256 == 0) return launch_tc<256>(p, stream);

@@ -102,6 +102,7 @@ int ppue_launch(const PpueArgs& a, int B, cudaStream_t stream) {
     dim3 grid(2 * a.num_max_points, B);
     ppue_kernel<<<grid, 128, 0, stream>>>(a);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -163,12 +164,14 @@ int coord_features_launch(const CoordArgs& a, int B, float* out, cudaStream_t st
     dim3 grid(a.H, B);
     coord_features_kernel<<<grid, 256, 0, stream>>>(a, out);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
 // grid (H, B), block W/2 threads: each thread converts a horizontal pixel pair of all 6 planes.
-// A[m = (b, y/p, x/p), k = c*p*p + (y%p)*p + x%p];  planes: R, G, B (raw, normalisation is folded
-// into the packed weights), prev mask, positive disks, negative disks.
+// A[m = (b, y/p, x/p), k = c*p*p + (y%p)*p + x%p];  planes c = 0..5: R, G, B (raw, normalisation is
+// folded into the packed weights), prev mask, positive disks, negative disks, all as bf16 "hi" parts;
+// planes 6..9: the bf16 "lo" residuals of R, G, B, prev mask ({0,1} disks are exact).  Row = 10*p*p.
 __global__ void __launch_bounds__(256) patch_operand_kernel(const CoordArgs a, __nv_bfloat16* __restrict__ A, int p,
                                                             int lda) {
     __shared__ SmemPoints sp;
@@ -182,8 +185,12 @@ __global__ void __launch_bounds__(256) patch_operand_kernel(const CoordArgs a, _
         __nv_bfloat16* dst = A + ((size_t)b * g * (H / p) + (size_t)gy * g + gx) * lda + ph * p + pw;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+            // split-bf16: v = hi + lo with |lo| <= 2^-9 |v|, so the patch-embed GEMM sees ~16 mantissa bits
             const float2 v = *reinterpret_cast<const float2*>(a.image4 + (((size_t)b * 4 + c) * H + y) * W + x);
-            *reinterpret_cast<uint32_t*>(dst + c * pp) = pack_bf16(v.x, v.y);
+            const uint32_t hi = pack_bf16(v.x, v.y);
+            const float2 hf = unpack_bf16(hi);
+            *reinterpret_cast<uint32_t*>(dst + c * pp) = hi;
+            *reinterpret_cast<uint32_t*>(dst + (6 + c) * pp) = pack_bf16(v.x - hf.x, v.y - hf.y);
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -206,6 +213,7 @@ int patch_operand_launch(const CoordArgs& a, int B, __nv_bfloat16* A, int patch,
     threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;
     patch_operand_kernel<<<grid, threads, 0, stream>>>(a, A, patch, lda);
     VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

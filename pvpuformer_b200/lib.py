@@ -20,6 +20,11 @@ class VpuDims(ctypes.Structure):
                 ("out_dims", c_int32 * 4), ("norm_radius", c_float)]
 
 
+class VpuProfileEntry(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("ms", c_double), ("flops", c_double), ("bytes", c_double),
+                ("launches", c_int64)]
+
+
 class VpuPrompts(ctypes.Structure):
     _fields_ = [("points", c_void_p), ("ppue_points", c_void_p), ("n", c_int32), ("n_ppue", c_int32),
                 ("type", c_int32), ("boxes", c_void_p), ("scrib_sel", c_void_p), ("scrib_slot", c_void_p),
@@ -30,6 +35,9 @@ class VpuPrompts(ctypes.Structure):
 SIGNATURES = {
     "vpu_last_error": (c_char_p, []),
     "vpu_version": (c_int, []),
+    "vpu_launch_count": (ctypes.c_ulonglong, []),
+    "vpu_profile_begin": (c_int, [c_void_p]),
+    "vpu_profile_end": (c_int, [c_void_p, POINTER(VpuProfileEntry), c_int, POINTER(c_int)]),
     "vpu_create": (c_int, [POINTER(c_void_p), POINTER(VpuDims)]),
     "vpu_destroy": (None, [c_void_p]),
     "vpu_bind_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64), c_int]),

@@ -61,7 +61,13 @@ def pack_weights(sd, cfg, device):
     std = torch.tensor(cfg.norm_std, device=device).view(1, 3, 1, 1)
     w_img = f["backbone.patch_embed.proj.weight"]                # [C,3,p,p]
     w_crd = f["patch_embed_coords.proj.weight"]
-    W("pe.w", torch.cat([(w_img / std).reshape(C, -1), w_crd.reshape(C, -1)], dim=1))
+    w_pe = torch.cat([(w_img / std).reshape(C, -1), w_crd.reshape(C, -1)], dim=1)     # [C, 6pp] fp32
+    w_hi = w_pe.to(bf)
+    pp = p * p
+    # split-bf16 (prompt.cu patch_operand_kernel): A = [hi planes (6pp) | lo planes of R,G,B,prev (4pp)];
+    # GEMM 1: A x [W_hi | W_hi[:, :4pp]], GEMM 2: A[:, :6pp] x W_lo
+    W("pe.w", torch.cat([w_hi, w_hi[:, :4 * pp]], dim=1))
+    W("pe.w_lo", w_pe - w_hi.float())
     fold = (w_img * (mean / std)).sum(dim=(1, 2, 3))             # [C]
     tab = f["backbone.pos_embed"][0, 1:] + (f["backbone.patch_embed.proj.bias"] + f["patch_embed_coords.proj.bias"] - fold)
     F32("pe.tab", tab)

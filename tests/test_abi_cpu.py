@@ -68,7 +68,8 @@ def test_module_surface_and_packing_shapes(arch):
         m.load_state_dict(sd, strict=True)
         packed, scalars = pack_weights(m.state_dict(), cfg, torch.device("cpu"))
         C, N = cfg.embed_dim, cfg.num_tokens
-        assert packed["pe.w"].shape == (C, 6 * cfg.patch ** 2) and packed["pe.w"].dtype == torch.bfloat16
+        assert packed["pe.w"].shape == (C, 10 * cfg.patch ** 2) and packed["pe.w"].dtype == torch.bfloat16
+        assert packed["pe.w_lo"].shape == (C, 6 * cfg.patch ** 2)
         assert packed["pe.tab"].shape == (N, C)
         assert packed["ffn.w1"].shape == (2048, 904) and not packed["ffn.w1"][:, 899:].any()
         assert packed["dma0.img.w"].shape == (3 * C // 2, C) and packed["dma0.img.tab"].shape == (N, 3 * C // 2)
