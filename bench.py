@@ -256,7 +256,7 @@ def main():
                "ms_per_step": ms_e / args.steps,
                "call": "VitMultiGaussianVector_ed_Model.forward(image, points) with pinned host tensors; D2H of 'instances'"}
 
-    classes = profile_classes(model, L, args.profile_steps, step_resident) if rank == 0 else []
+    classes = profile_classes(model, L, args.profile_steps, step_resident) if (rank == 0 and args.profile_steps > 0) else []
     if world > 1:
         dist.barrier()
     if rank != 0:

@@ -459,18 +459,19 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         hca.res[i] = (int)res[i];
     }
     hca.bias = f.Wf("hd.f.b"); hca.out = f.buf<bf>("F"); hca.rnorm = f.buf<float>("rnorm"); hca.B = B;
+    hca.wseg = f.Wf("hd.seg.w"); hca.seg_bias = h.scalars.at("hd.seg.b"); hca.seg_out = f.buf<float>("seg_low");
     RUN(f.timed("head_combine", 0, (double)B * hc * 2.0 * (2.0 * g4 * g4 + g2 * g2 + (double)g * g + gh * gh), [&] { return head_combine_launch(hca, s); }));
-    RUN(f.gemm(f.buf<bf>("qout_b"), C, "hd.q.w1", MQ, 2 * C, C, f.Wf("hd.q.b1"), f.buf<bf>("QF"), true, 2 * C, ACT_RELU));
-    RUN(f.gemm(f.buf<bf>("QF"), 2 * C, "hd.q.w2", MQ, hc, 2 * C, f.Wf("hd.q.b2"), f.buf<float>("QE"), false, hc));
-    RUN(f.timed("head_queries", 0, (double)B * 64 * hc * 6.0, [&] { return head_queries_launch(f.buf<float>("QE"), f.Wf("hd.seg.w"), B, Q, f.buf<bf>("QN"), s); }));
-    {
+    if (aux) {   // P2CL cosine logits (swin_transformer.py:745-756); skipped when the caller only reads 'instances'
+        RUN(f.gemm(f.buf<bf>("qout_b"), C, "hd.q.w1", MQ, 2 * C, C, f.Wf("hd.q.b1"), f.buf<bf>("QF"), true, 2 * C, ACT_RELU));
+        RUN(f.gemm(f.buf<bf>("QF"), 2 * C, "hd.q.w2", MQ, hc, 2 * C, f.Wf("hd.q.b2"), f.buf<float>("QE"), false, hc));
+        RUN(f.timed("head_queries", 0, (double)B * 64 * hc * 6.0, [&] { return head_queries_launch(f.buf<float>("QE"), f.Wf("hd.seg.w"), B, Q, f.buf<bf>("QN"), s); }));
         GemmProblem p;
         p.A = f.buf<bf>("F"); p.W = f.buf<bf>("QN"); p.M = (int)(B * g4 * g4); p.N = 64; p.K = hc; p.lda = hc; p.ldw = hc;
         p.w_rows = B * 64;
         p.epi.mode = EPI_HEAD_FINAL; p.epi.m_per_batch = (int)(g4 * g4); p.epi.b_rows_per_batch = 64;
-        p.epi.rnorm = f.buf<float>("rnorm"); p.epi.aux_out = aux ? f.buf<float>("aux_low") : nullptr;
-        p.epi.seg_out = f.buf<float>("seg_low"); p.epi.seg_bias = h.scalars.at("hd.seg.b"); p.epi.nq = Q;
-        const double by = (double)p.M * (hc * 2.0 + 4.0 + (aux ? Q * 4.0 : 0.0) + 4.0);
+        p.epi.rnorm = f.buf<float>("rnorm"); p.epi.aux_out = f.buf<float>("aux_low");
+        p.epi.seg_out = nullptr; p.epi.seg_bias = 0.f; p.epi.nq = Q;
+        const double by = (double)p.M * (hc * 2.0 + 4.0 + Q * 4.0);
         RUN(f.timed("gemm", 2.0 * p.M * 64.0 * hc, by, [&] { return gemm_launch(p, s, h.gemm_impl); }));
     }
     // ---- A17: final upsampling (align_corners=True) ----

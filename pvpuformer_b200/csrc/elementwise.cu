@@ -298,10 +298,16 @@ __global__ void __launch_bounds__(256) head_combine_kernel(const HeadCombineArgs
         acc8(f, base + ((size_t)y1 * r + x0) * 256, ly * (1.f - lx));
         acc8(f, base + ((size_t)y1 * r + x1) * 256, ly * lx);
     }
-    float ss = 0.f;
+    float ss = 0.f, seg = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { f[k] = fmaxf(f[k], 0.f); ss += f[k] * f[k]; }
+    for (int k = 0; k < 8; ++k) {
+        f[k] = fmaxf(f[k], 0.f);
+        ss += f[k] * f[k];
+        seg += f[k] * __ldg(a.wseg + c + k);     // conv_seg (decode_head.py:210-215) in fp32, before the bf16 store
+    }
     ss = warp_sum(ss);
+    seg = warp_sum(seg);
+    if (lane == 0) a.seg_out[pix] = seg + a.seg_bias;
     *reinterpret_cast<uint4*>(a.out + pix * 256 + c) =
         make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     if (lane == 0) a.rnorm[pix] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);

@@ -45,6 +45,9 @@ struct HeadCombineArgs {
     const float* bias = nullptr;     // fusion conv bias [256]
     __nv_bfloat16* out = nullptr;    // [B*res0^2, 256]
     float* rnorm = nullptr;          // [B*res0^2]
+    const float* wseg = nullptr;     // conv_seg weight [256] fp32
+    float seg_bias = 0.f;
+    float* seg_out = nullptr;        // [B*res0^2] fp32: conv_seg(f) evaluated on the un-rounded fp32 features
     int B = 0;
 };
 int head_combine_launch(const HeadCombineArgs& a, cudaStream_t stream);

@@ -63,7 +63,7 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n0, float (&v
             const int n = n0 + t;
             if (n < e.nq) {
                 if (e.aux_out) e.aux_out[((size_t)b * e.nq + n) * e.m_per_batch + pix] = (v[t] * rn + 1.0f) * 0.5f;
-            } else if (n == e.nq) {
+            } else if (n == e.nq && e.seg_out) {
                 e.seg_out[(size_t)b * e.m_per_batch + pix] = v[t] + e.seg_bias;
             }
         }

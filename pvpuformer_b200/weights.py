@@ -128,17 +128,31 @@ def _gen(key, seed):
     return g
 
 
-def synthetic_tensor(key, shape, seed=0):
-    """Deterministic fp32 tensor for one state_dict entry (see module docstring)."""
+def synthetic_tensor(key, shape, seed=0, scheme="reference_init"):
+    """Deterministic fp32 tensor for one state_dict entry (see module docstring).
+
+    scheme="reference_init" follows the distributions the reference's constructors draw from:
+    xavier-uniform for every ViT Linear and the image patch embed (models_vit.py:169-188), torch's
+    default U(+-1/sqrt(fan_in)) for the DMA / neck / head Linear and Conv layers (plain nn.Linear,
+    nn.Conv2d, nn.ConvTranspose2d; the ConvModule stand-in of SURVEY.md 8c), N(0, .02) pos_embed.
+    Unlike the reference, biases and norm affines are small random values instead of 0 / 1 so that
+    every parameter of the path is exercised by the parity tests.
+    scheme="xavier" uses xavier-uniform everywhere (about 8x larger logits: the stress set)."""
     g = _gen(key, seed)
     if key == "head.logit_scale":
         return torch.tensor(math.log(1 / 0.07), dtype=torch.float32)
-    if len(shape) >= 2 and key.endswith(".weight") and "embed" not in key.split(".")[0]:
+    dead_table = key.split(".")[0] in ("point_embeddings", "not_a_point_embed")     # nn.Embedding: N(0, 1)
+    if len(shape) >= 2 and key.endswith(".weight") and not dead_table:
         rf = 1
         for d in shape[2:]:
             rf *= d
         fan_in, fan_out = shape[1] * rf, shape[0] * rf
-        a = math.sqrt(6.0 / (fan_in + fan_out))
+        if key == "backbone.patch_embed.proj.weight" and scheme != "xavier":
+            fan_out = shape[0]                              # xavier on w.view(C, -1) (models_vit.py:169-171)
+        if scheme == "xavier" or key.startswith("backbone."):
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+        else:
+            a = 1.0 / math.sqrt(fan_in)
         return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * a
     if key.endswith("pos_embed") or key.endswith("cls_token"):
         return torch.randn(shape, generator=g, dtype=torch.float32) * 0.02
@@ -149,5 +163,5 @@ def synthetic_tensor(key, shape, seed=0):
     return torch.randn(shape, generator=g, dtype=torch.float32)
 
 
-def synthetic_state_dict(cfg: VPUConfig, seed=0):
-    return OrderedDict((k, synthetic_tensor(k, shape, seed)) for k, (shape, _) in param_spec(cfg).items())
+def synthetic_state_dict(cfg: VPUConfig, seed=0, scheme="reference_init"):
+    return OrderedDict((k, synthetic_tensor(k, shape, seed, scheme)) for k, (shape, _) in param_spec(cfg).items())

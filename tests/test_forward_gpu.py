@@ -17,17 +17,26 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 2e-2     # north_star: bf16 logits within 2e-2 abs
 AUX_TOL = 2e-2
+REL_MAX = 0.15       # max|d| / std(reference logits): the discriminating gates (bf16 floor measured at ~0.06-0.12)
+REL_MEAN = 0.02
 _MODELS = {}
 
 
-def _model(arch):
+def _model(arch, scheme="reference_init"):
     from pvpuformer_b200.model import build_model
-    if arch not in _MODELS:
+    if (arch, scheme) not in _MODELS:
         _MODELS.clear()
         torch.cuda.empty_cache()
-        sd = synthetic_state_dict(make_config(arch), 0)
-        _MODELS[arch] = (build_model(arch, state_dict=sd, device=torch.device("cuda:0")), sd)
-    return _MODELS[arch]
+        sd = synthetic_state_dict(make_config(arch), 0, scheme)
+        _MODELS[(arch, scheme)] = (build_model(arch, state_dict=sd, device=torch.device("cuda:0")), sd)
+    return _MODELS[(arch, scheme)]
+
+
+def _rel_gates(got, ref, rel_max=REL_MAX, rel_mean=REL_MEAN):
+    d = (got - ref).abs()
+    std = ref.std().item()
+    assert d.max().item() <= rel_max * std, (d.max().item(), std)
+    assert d.mean().item() <= rel_mean * std, (d.mean().item(), std)
 
 
 def _iou(a, b):
@@ -76,7 +85,8 @@ def test_forward_vs_reference_golden_vit_base(name):
     got = inst[:, :, ::4, ::4]
     assert _iou(torch.sigmoid(got) > 0.49, torch.sigmoid(ref) > 0.49) >= 0.999
     med = ref.median()
-    assert _iou(got > med, ref > med) >= 0.99
+    assert _iou(got > med, ref > med) >= 0.98
+    _rel_gates(got, ref)
 
 
 @pytest.mark.parametrize("arch", ["vit_large", "vit_huge"])
@@ -89,6 +99,22 @@ def test_forward_vs_reference_golden_large_huge(arch):
     assert np.abs(out["instances"][:, 0, 100, :].cpu().numpy() - g["instances_row100"]).max() <= LOGIT_TOL
     seg_low = m.tap("seg_low", 2, torch.float32, (2, 1, g4, g4)).cpu().numpy()
     assert np.abs(seg_low - g["seg_lowres"]).max() <= LOGIT_TOL
+
+
+def test_forward_vs_oracle_stress_weights_relative_error():
+    """xavier-everywhere weights give ~8x larger logits (std ~0.2): the absolute gate no longer has the
+    10x headroom it has at the reference's init scale, so the error is gated relative to the logit std."""
+    m, sd = _model("vit_base", "xavier")
+    image4 = cases.images(3, seed=31)
+    pts = cases.random_clicks(3, seed=32, dtype=torch.float64)
+    with torch.no_grad():
+        ref = vo.forward(sd, m.cfg, image4, pts)
+    out = m(image4.cuda(), pts.cuda())
+    # conv_seg sums 256 non-negative features with zero-mean weights (|seg| ~ 0.03 sum|w f|), so this set
+    # amplifies the bf16 floor of the features more than the reference-init set does: measured 0.037 / 0.10
+    _rel_gates(out["instances"].cpu(), ref["instances"], rel_max=0.2, rel_mean=0.05)
+    med = ref["instances"].median()
+    assert _iou(out["instances"].cpu() > med, ref["instances"] > med) >= 0.97
 
 
 def test_forward_vs_oracle_fresh_inputs_and_batch_independence():
@@ -104,6 +130,7 @@ def test_forward_vs_oracle_fresh_inputs_and_batch_independence():
     d = (out["instances"].cpu() - ref["instances"]).abs().max().item()
     da = (out["instances_aux"].cpu() - ref["instances_aux"]).abs().max().item()
     assert d <= LOGIT_TOL and da <= AUX_TOL, (d, da)
+    _rel_gates(out["instances"].cpu(), ref["instances"])
     a, b = torch.sigmoid(out["instances"].cpu()) > 0.49, torch.sigmoid(ref["instances"]) > 0.49
     assert _iou(a, b) >= 0.999
     solo = m(image4[:1].cuda(), pts[:1].cuda())["instances"]
