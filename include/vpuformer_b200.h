@@ -110,7 +110,7 @@ int vpu_coord_features(vpu_handle h, const float* image4, const vpu_prompts* pro
 /* out[M,N] = act(A[M,K] * W[N,K]^T + bias[N] + bias2d[m % rows, N] + residual[M,N]) */
 int vpu_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* bias,
              const float* bias2d, int bias2d_rows, const void* residual, int residual_dtype, int ldr, int act /*0,1 gelu,2 relu*/,
-             void* out, int out_dtype, int ldo, int impl /*0 tcgen05, 1 mma.sync cross-check*/, void* stream);
+             void* out, int out_dtype, int ldo, int impl /*0 tcgen05 (2-CTA pairs when the shape allows), 1 mma.sync cross-check, 2 tcgen05 1-CTA*/, void* stream);
 /* ConvTranspose2d(k=2,s=2) as GEMM + pixel-shuffle store: A [B*g*g, K] -> out NHWC [B, 2g, 2g, cout] bf16 */
 int vpu_gemm_pixel_shuffle(const void* A_bf16, const void* W_bf16, int M, int cout, int K, const float* bias4, int g,
                            void* out_bf16, int impl, void* stream);

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -39,8 +40,16 @@ unsigned long long launch_count() { return g_launches.load(std::memory_order_rel
 template <int CNT>
 __device__ __forceinline__ void epi_store(const Epi& e, int m, int n0, float (&v)[CNT], int N) {
     if (e.bias) {
+        if constexpr (CNT % 4 == 0) {
 #pragma unroll
-        for (int t = 0; t < CNT; ++t) v[t] += __ldg(e.bias + n0 + t);
+            for (int t = 0; t < CNT; t += 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + t));
+                v[t] += x.x; v[t + 1] += x.y; v[t + 2] += x.z; v[t + 3] += x.w;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < CNT; ++t) v[t] += __ldg(e.bias + n0 + t);
+        }
     }
     if (e.bias2d) {
         const float* b2 = e.bias2d + (size_t)(m % e.bias2d_rows) * N + n0;
@@ -140,6 +149,155 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n0, float (&v
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tile epilogue of the tcgen05 kernels.  tcgen05.ld hands every thread ONE accumulator row
+// (32 consecutive columns), which makes direct global access row-strided: 32 lanes touch 32
+// different lines per instruction (round-1 profile: the K=768 GEMMs were epilogue-bound).  Each
+// epilogue warp therefore transposes its 32x32 chunk through a private padded shared-memory buffer
+// (pitch 36 words: conflict-free 16-byte row writes and row reads) and then works row-major:
+// 8 lanes x 4 columns cover one row, so a warp instruction touches 4 rows x 64-128 contiguous
+// bytes, residual / table loads and stores are full-sector, and the residual loads of a whole
+// chunk are in flight before the accumulator arrives.
+// The epilogue is specialised at compile time (EpiKind): with every variant behind run-time flags
+// the row loop was ~20 instructions per 64 elements plus uniform branches, and with only two
+// epilogue warps per scheduler that issue stream -- not memory -- bounded the K=768 GEMMs.
+// ------------------------------------------------------------------------------------------
+struct GemmDims {
+    int M, N, K;
+    int stages;   // pipeline depth actually used (<= the compiled maximum; VPU_GEMM_STAGES experiment knob)
+    int ablate;   // measurement only (VPU_GEMM_ABLATE): 1 = no TMA loads (stale operands), 2 = no MMA issue; results are garbage
+};
+
+enum EpiKind {
+    EK_BF16 = 0,       // out bf16 = acc + bias                       (qkv, DMA / neck / head-Y projections)
+    EK_BF16_GELU = 1,  // out bf16 = gelu(acc + bias)                 (ViT fc1)
+    EK_BF16_RELU = 2,  // out bf16 = relu(acc + bias)                 (FFNs, head convs)
+    EK_F32_RES = 3,    // out fp32 = acc + bias + residual fp32       (ViT proj / fc2 on the residual stream)
+    EK_GENERIC = 4,    // everything behind run-time flags            (tables, pixel shuffle, bf16 residual ...)
+    EK_HEAD = 5        // EPI_HEAD_FINAL                              (P2CL logits, 1-CTA BN=64 only)
+};
+
+constexpr int EPI_PITCH = 36;                        // fp32 words per staged row
+constexpr int EPI_WARP_WORDS = 32 * EPI_PITCH;       // 4608 B per epilogue warp
+constexpr int EPI_SMEM_BYTES = 8 * EPI_WARP_WORDS * 4;
+
+// erf-GELU (reference nn.GELU(), models_vit.py:14-27) with erf from Abramowitz-Stegun 7.1.28,
+// erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |error| <= 3e-7: 16 instructions and one MUFU instead of
+// the ~30-instruction branchy erff; the bf16 output keeps 8 mantissa bits.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float p = 0.0000430638f;
+    p = fmaf(p, z, 0.0002765672f);
+    p = fmaf(p, z, 0.0001520143f);
+    p = fmaf(p, z, 0.0092705272f);
+    p = fmaf(p, z, 0.0422820123f);
+    p = fmaf(p, z, 0.0705230784f);
+    p = fmaf(p, z, 1.0f);
+    p = p * p; p = p * p; p = p * p; p = p * p;
+    float rp;   // rcp.approx: one MUFU, 1 ulp, no range-check slow path (p >= 1; inf -> 0), so the four
+                // GELUs of a lane stay branch-free and interleave (__frcp_rn serialised them behind BSSY/CALL)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rp) : "f"(p));
+    const float erf_abs = 1.0f - rp;
+    const float h = 0.5f * x;
+    return fmaf(h, copysignf(erf_abs, x), h);
+}
+
+template <int BN, int EK>
+__device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, uint32_t tmem_acc, int row_base, int col_base,
+                                              int quarter, int half, int lane, float* sbuf) {
+    const int r_lo = row_base + quarter * 32;
+    if constexpr (EK == EK_HEAD) {   // column-major NCHW stores: lane == row is already the coalesced mapping
+        const int row = r_lo + lane;
+#pragma unroll 1
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
+            tmem_ld_wait();
+            const int n0 = col_base + c;
+            if (row < d.M && n0 < d.N) {
+                float v[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
+                epi_store<32>(e, row, n0, v, d.N);
+            }
+        }
+    } else {
+        constexpr bool DYN = EK == EK_GENERIC;
+        const bool has_res = DYN ? (e.res != nullptr) : (EK == EK_F32_RES);
+        const bool res_bf16 = DYN ? (e.res_bf16 != 0) : false;
+        const bool out_bf16 = DYN ? (e.out_bf16 != 0) : (EK != EK_F32_RES);
+        const int act = DYN ? e.act : (EK == EK_BF16_GELU ? ACT_GELU : (EK == EK_BF16_RELU ? ACT_RELU : ACT_NONE));
+        const bool has_tab = DYN && e.bias2d != nullptr;
+        const bool pshuf = DYN && e.mode == EPI_PIXEL_SHUFFLE;
+        const int sub = lane >> 3, j4 = (lane & 7) * 4;
+#pragma unroll 1
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+            const int n0 = col_base + c;
+            if (n0 >= d.N) break;                     // N is a multiple of 32: chunks are all-valid or all-outside
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
+            const int n = n0 + j4;
+            // operands that do not depend on the accumulator are requested while the TMEM load is in flight
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.bias) bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+            float4 res[8];
+            if (has_res) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int m = r_lo + 4 * it + sub;
+                    res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m < d.M) {
+                        if (res_bf16) {
+                            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.res) + (size_t)m * e.ldr + n);
+                            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+                            res[it] = make_float4(a.x, a.y, b.x, b.y);
+                        } else {
+                            res[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.res) + (size_t)m * e.ldr + n);
+                        }
+                    }
+                }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(sbuf + lane * EPI_PITCH + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = 4 * it + sub, m = r_lo + rr;
+                float4 v = *reinterpret_cast<const float4*>(sbuf + rr * EPI_PITCH + j4);
+                if (m < d.M) {
+                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
+                    if (has_tab) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias2d + (size_t)(m % e.bias2d_rows) * d.N + n));
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    }
+                    if (act == ACT_GELU) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
+                    else if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    size_t orow = (size_t)m;
+                    int ocol = n;
+                    if (pshuf) {
+                        const int g = e.ps_g, gg = g * g;
+                        const int b = m / gg, ij = m % gg, i = ij / g, jx = ij % g;
+                        const int q = n / e.ps_cout;
+                        ocol = n % e.ps_cout;
+                        orow = ((size_t)b * 2 * g + 2 * i + (q >> 1)) * (size_t)(2 * g) + 2 * jx + (q & 1);
+                    }
+                    if (out_bf16)
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + orow * e.ldo + ocol) =
+                            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                    else
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + orow * e.ldo + ocol) = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------
@@ -148,20 +306,16 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 320;
 
 template <int BN> struct TileCfg {
-    static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+    static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : (BN == 128 ? 5 : 7));
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024;  // + alignment slack
 };
 
-struct GemmDims {
-    int M, N, K;
-};
-
-template <int BN>
+template <int BN, int EK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDims d,
                const Epi e) {
@@ -257,20 +411,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_blk = tile / n_blks, n_blk = tile % n_blks;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * BM + quarter * 32 + lane;
-#pragma unroll 1
-            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_STRIDE + c, r);
-                tmem_ld_wait();
-                const int n0 = n_blk * BN + c;
-                if (row < d.M && n0 < d.N) {
-                    float v[32];
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
-                    epi_store<32>(e, row, n0, v, d.N);
-                }
-            }
+            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, m_blk * BM, n_blk * BN, quarter, half, lane,
+                              reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES) + (warp - 2) * EPI_WARP_WORDS);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -283,6 +425,149 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA tcgen05 kernel: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 (M = 256).  Each CTA loads its own 128 rows of A and HALF of the B tile,
+// so the L2 -> shared-memory traffic per MMA-flop drops to 2/3 of the 1-CTA kernel (the 1-CTA 128x256
+// tile needs ~96 B/clk/SM, above the measured ~6.3 KB/clk chip-wide L2 cap; B300_MICROARCH.md "L2").
+// Roles per CTA as above; only the leader's warp 1 issues MMAs.  Barriers:
+//   full[s]   leader only, tx = both CTAs' loads (peer TMA signals the leader's barrier)
+//   empty[s]  one per CTA, released by the leader's multicast tcgen05.commit
+//   tfull[a]  one per CTA (multicast commit);  tempty[a] leader only, 16 arrivals (8 epilogue warps x 2 CTAs)
+// ------------------------------------------------------------------------------------------
+template <int BN> struct TileCfg2 {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = BN == 256 ? 5 : 7;
+    static constexpr int ACC_STRIDE = BN;   // 256 or 128 columns per accumulator buffer
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024;
+};
+
+template <int BN, int EK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDims d,
+                const Epi e) {
+    using C = TileCfg2<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 16);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2sm(&tmem_base_smem, C::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();     // barriers of both CTAs initialised before any remote arrive / TMA signal
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int n_blks = (d.N + BN - 1) / BN;
+    const int m_blks = (d.M + 2 * BM - 1) / (2 * BM);
+    const int tiles = n_blks * m_blks;
+    const int kblks = (d.K + BK - 1) / BK;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int nst = d.stages > 0 && d.stages < C::STAGES ? d.stages : C::STAGES;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- TMA producer (both CTAs) ----------------
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < tiles; tile += npairs) {
+                const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+                const int arow = m_blk * 2 * BM + (int)rank * BM;
+                const int brow = n_blk * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < kblks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (d.ablate & 1) {
+                        if (leader) mbar_arrive(&full_bar[stage]);
+                    } else {
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                        tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, arow);
+                        tma_load_2d_2sm(sa + C::A_BYTES, &tmB, &full_bar[stage], kb * BK, brow);
+                    }
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ---------------- MMA issuer (leader CTA only) ----------------
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < tiles; tile += npairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
+                for (int kb = 0; kb < kblks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + C::A_BYTES;
+                    if (!(d.ablate & 2))
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty_bar[stage], 3);   // frees this stage in BOTH CTAs
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull_bar[acc], 3);         // accumulator halves complete in both CTAs
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {  // ---------------- epilogue warps (both CTAs: own 128 rows, all BN columns) ----------------
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < tiles; tile += npairs) {
+            const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, m_blk * 2 * BM + (int)rank * BM, n_blk * BN, quarter, half,
+                              lane, reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES) + (warp - 2) * EPI_WARP_WORDS);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();     // the peer's shared memory / barriers stay alive until every MMA and commit has landed
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -352,6 +637,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
+static bool g_use_2cta = true;
+static int g_stages = 0;
+static int g_ablate = 0;
 static std::mutex g_mu;
 
 struct TmKey {
@@ -371,6 +659,31 @@ struct TmKeyHash {
 };
 static std::unordered_map<TmKey, CUtensorMap, TmKeyHash> g_tm_cache;
 
+template <int BN, int EK> static int attr1() {
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::SMEM_BYTES));
+    return 0;
+}
+template <int BN, int EK> static int attr2() {
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg2<BN>::SMEM_BYTES));
+    return 0;
+}
+template <int BN> static int attrs2_all() {
+    if (int rc = attr2<BN, EK_BF16>()) return rc;
+    if (int rc = attr2<BN, EK_BF16_GELU>()) return rc;
+    if (int rc = attr2<BN, EK_BF16_RELU>()) return rc;
+    if (int rc = attr2<BN, EK_F32_RES>()) return rc;
+    return attr2<BN, EK_GENERIC>();
+}
+static int set_smem_attrs() {
+    if (int rc = attr1<64, EK_HEAD>()) return rc;
+    if (int rc = attr1<64, EK_GENERIC>()) return rc;
+    if (int rc = attr1<128, EK_GENERIC>()) return rc;
+    if (int rc = attr1<192, EK_GENERIC>()) return rc;
+    if (int rc = attr1<256, EK_GENERIC>()) return rc;
+    if (int rc = attrs2_all<256>()) return rc;
+    return attrs2_all<128>();
+}
+
 int gemm_init() {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_encode) return 0;
@@ -385,10 +698,11 @@ int gemm_init() {
     VPU_REQUIRE(prop.major == 10, "pvpuformer_b200 needs an sm_100a device (got sm_%d%d): no fallback path exists",
                 prop.major, prop.minor);
     g_num_sms = prop.multiProcessorCount;
-    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<64>::SMEM_BYTES));
-    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::SMEM_BYTES));
-    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<192>::SMEM_BYTES));
-    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES));
+    if (int rc = set_smem_attrs()) return rc;
+    const char* two = getenv("VPU_GEMM_2CTA");
+    g_use_2cta = !(two && two[0] == '0');
+    if (const char* st = getenv("VPU_GEMM_STAGES")) g_stages = atoi(st);
+    if (const char* ab = getenv("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
@@ -419,18 +733,52 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t c
     return 0;
 }
 
-template <int BN>
+template <int BN, int EK = EK_GENERIC>
 static int launch_tc(const GemmProblem& p, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap(&tmA, p.A, p.M, p.K, p.lda, BM)) return rc;
     if (int rc = make_tmap(&tmB, p.W, p.w_rows ? p.w_rows : p.N, p.K, p.ldw, BN)) return rc;
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    GemmDims d{p.M, p.N, p.K};
-    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d, p.epi);
+    GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
+    gemm_tc_kernel<BN, EK><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d, p.epi);
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
+}
+
+template <int BN, int EK>
+static int launch_tc2_k(const GemmProblem& p, cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    if (int rc = make_tmap(&tmA, p.A, p.M, p.K, p.lda, BM)) return rc;
+    if (int rc = make_tmap(&tmB, p.W, p.w_rows ? p.w_rows : p.N, p.K, p.ldw, BN / 2)) return rc;
+    const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
+    const int max_pairs = g_num_sms / 2;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
+    gemm_tc2_kernel<BN, EK><<<2 * pairs, GEMM_THREADS, TileCfg2<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d, p.epi);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+// pick the compile-time epilogue the problem's run-time flags describe
+static int epi_kind(const Epi& e) {
+    if (e.mode != EPI_PLAIN || e.bias2d) return EK_GENERIC;
+    if (e.out_bf16 && !e.res) return e.act == ACT_GELU ? EK_BF16_GELU : (e.act == ACT_RELU ? EK_BF16_RELU : EK_BF16);
+    if (!e.out_bf16 && e.res && !e.res_bf16 && e.act == ACT_NONE) return EK_F32_RES;
+    return EK_GENERIC;
+}
+
+template <int BN>
+static int launch_tc2(const GemmProblem& p, cudaStream_t stream) {
+    switch (epi_kind(p.epi)) {
+        case EK_BF16: return launch_tc2_k<BN, EK_BF16>(p, stream);
+        case EK_BF16_GELU: return launch_tc2_k<BN, EK_BF16_GELU>(p, stream);
+        case EK_BF16_RELU: return launch_tc2_k<BN, EK_BF16_RELU>(p, stream);
+        case EK_F32_RES: return launch_tc2_k<BN, EK_F32_RES>(p, stream);
+        default: return launch_tc2_k<BN, EK_GENERIC>(p, stream);
+    }
 }
 
 int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
@@ -445,7 +793,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
     if (p.epi.mode == EPI_PIXEL_SHUFFLE)
         VPU_REQUIRE(p.epi.ps_cout % 32 == 0 && p.N == 4 * p.epi.ps_cout, "pixel-shuffle GEMM needs N == 4*cout, cout %% 32 == 0");
     if (impl == 1) {
-        GemmDims d{p.M, p.N, p.K};
+        GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
         dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
         if (p.epi.m_per_batch > 0) VPU_REQUIRE(p.epi.m_per_batch % 64 == 0, "m_per_batch must be a multiple of 64");
         gemm_mma_kernel<<<grid, 128, 0, stream>>>(p.A, p.W, p.lda, p.ldw, d, p.epi);
@@ -453,6 +801,12 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         count_launch();
         return 0;
     }
+    // impl 0: 2-CTA pairs whenever the shape allows it; impl 2 forces the 1-CTA kernel (A/B comparison, tests)
+    if (impl == 0 && g_use_2cta && p.epi.mode != EPI_HEAD_FINAL && p.M >= 2 * BM) {
+        if (p.N % 256 == 0) return launch_tc2<256>(p, stream);
+        if (p.N % 128 == 0) return launch_tc2<128>(p, stream);
+    }
+    if (p.epi.mode == EPI_HEAD_FINAL) return launch_tc<64, EK_HEAD>(p, stream);
     if (p.N % 256 == 0) return launch_tc<256>(p, stream);
     if (p.N % 192 == 0) return launch_tc<192>(p, stream);
     if (p.N % 128 == 0) return launch_tc<128>(p, stream);

@@ -34,7 +34,7 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_plain(M, N, K, impl):
     from pvpuformer_b200 import ops
@@ -46,7 +46,7 @@ def test_gemm_plain(M, N, K, impl):
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_gemm_epilogues(impl):
     from pvpuformer_b200 import ops
     M, N, K = 1568, 768, 256
@@ -79,7 +79,7 @@ def test_gemm_epilogues(impl):
     assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_gemm_pixel_shuffle_matches_conv_transpose(impl):
     from pvpuformer_b200 import ops
     B, g, cin, cout = 2, 28, 256, 192
