@@ -8,6 +8,8 @@
 // accumulate), K/V tiles double-buffered with cp.async, scores never leave registers.
 // Q/K/V are read in place from the projection outputs (row stride + column offset), so no
 // head split / window partition copies exist.  CTA = 4 warps x 16 query rows.
+#include <cstdlib>
+
 #include "attention.cuh"
 
 namespace vpu {
@@ -229,6 +231,8 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
                     a.koff % 8 == 0 && a.voff % 8 == 0,
                 "attention strides/offsets must be multiples of 8 elements");
     VPU_REQUIRE(a.nprob <= 65535 && a.heads <= 65535, "attention grid too large");
+    static const bool use_tc = [] { const char* e = getenv("VPU_ATTN_TC"); return !(e && e[0] == '0'); }();
+    if (use_tc && window_attention_tc_supported(a, head_dim)) return window_attention_tc_launch(a, stream);
     switch (head_dim) {
         case 48: return launch_att<48>(a, stream);
         case 64: return launch_att<64>(a, stream);

@@ -28,4 +28,8 @@ struct AttnArgs {
 
 int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream);
 
+// tcgen05 / TMEM kernel for 14x14-token windows, head_dim 64 (attention_tc.cu)
+bool window_attention_tc_supported(const AttnArgs& a, int head_dim);
+int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
+
 }  // namespace vpu
