@@ -138,16 +138,26 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ partial, int chunk
         mean_rstd[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
     }
 }
+// apply: every thread owns one channel octet (gamma / beta live in registers) and strides over pixels
 __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ x, size_t per_sample, int C,
                                                        const float2* __restrict__ mean_rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int gelu) {
-    const int b = blockIdx.y;
+    const int b = blockIdx.y, C8 = C / 8, C8z = C8 / gridDim.z;      // wide layers split their channels over grid.z
+    const int co = blockIdx.z * C8z + threadIdx.x % C8z, prow = threadIdx.x / C8z, rows_per_block = blockDim.x / C8z;
     const float2 mr = mean_rstd[b];
+    float sc[8], sh[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + co * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + co * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + co * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + co * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = mr.y * g[k]; sh[k] = bb[k] - mr.x * mr.y * g[k]; }   // y = x*sc + sh
+    }
     uint4* p = reinterpret_cast<uint4*>(x + (size_t)b * per_sample);
-    const size_t n8 = per_sample / 8;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)((i * 8) % C);
+    const size_t npix = per_sample / C;
+    for (size_t pix = (size_t)blockIdx.x * rows_per_block + prow; pix < npix; pix += (size_t)gridDim.x * rows_per_block) {
+        const size_t i = pix * C8 + co;
         uint4 v = p[i];
         float f[8];
         float2 t;
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
         t = unpack_bf16(v.w); f[6] = t.x; f[7] = t.y;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float y = (f[k] - mr.x) * mr.y * __ldg(gamma + c + k) + __ldg(beta + c + k);
+            const float y = fmaf(f[k], sc[k], sh[k]);
             f[k] = gelu ? gelu_erf(y) : y;
         }
         v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]); v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
@@ -171,7 +181,15 @@ int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const fl
     if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
     gn_stats_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, per_sample, partial);
     gn_finalize_kernel<<<B, 32, 0, stream>>>(partial, chunks, (double)per_sample, 1e-5f, mean_rstd);
-    gn_apply_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, per_sample, C, mean_rstd, gamma, beta, gelu);
+    VPU_REQUIRE(per_sample % C == 0, "groupnorm: C must divide the sample size");
+    const int C8 = C / 8;
+    int zsplit = 1;
+    while (C8 / zsplit > 256 || C8 % zsplit) ++zsplit;
+    const int C8z = C8 / zsplit, threads = C8z * (256 / C8z);
+    const size_t npix = per_sample / C;
+    int blocks = (int)((npix + (threads / C8z) - 1) / (threads / C8z));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gn_apply_kernel<<<dim3(blocks, B, zsplit), threads, 0, stream>>>(x, per_sample, C, mean_rstd, gamma, beta, gelu);
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch(3);
     return 0;
@@ -282,8 +300,10 @@ __global__ void __launch_bounds__(256) head_combine_kernel(const HeadCombineArgs
     const int b = (int)(pix / ((size_t)R * R)), yx = (int)(pix % ((size_t)R * R)), y = yx / R, x = yx % R;
     const int c = lane * 8;
     float f[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = __ldg(a.bias + c + k);
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
+        f[0] = b0.x; f[1] = b0.y; f[2] = b0.z; f[3] = b0.w; f[4] = b1.x; f[5] = b1.y; f[6] = b1.z; f[7] = b1.w;
+    }
     acc8(f, a.y[0] + pix * 256 + c, 1.0f);
 #pragma unroll
     for (int l = 1; l < 4; ++l) {
@@ -299,11 +319,13 @@ __global__ void __launch_bounds__(256) head_combine_kernel(const HeadCombineArgs
         acc8(f, base + ((size_t)y1 * r + x1) * 256, ly * lx);
     }
     float ss = 0.f, seg = 0.f;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.wseg + c)), w1 = __ldg(reinterpret_cast<const float4*>(a.wseg + c + 4));
+    const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         f[k] = fmaxf(f[k], 0.f);
         ss += f[k] * f[k];
-        seg += f[k] * __ldg(a.wseg + c + k);     // conv_seg (decode_head.py:210-215) in fp32, before the bf16 store
+        seg += f[k] * ws[k];                     // conv_seg (decode_head.py:210-215) in fp32, before the bf16 store
     }
     ss = warp_sum(ss);
     seg = warp_sum(seg);
@@ -380,8 +402,68 @@ __global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restric
         reinterpret_cast<float4*>(out)[idx] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
+// 4 x 4 output block per thread: for the x4 scale of this path (112 -> 448, step 111/447 < 1/3) the 16 outputs read a
+// 3 x 3 source patch, so loads drop from 64 to 9 per block and the horizontal interpolation is shared by 4 rows.
+__global__ void __launch_bounds__(256) upsample_ac4_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                           int H, int W, size_t planes) {
+    const int W4 = W / 4, H4 = H / 4;
+    const size_t total = planes * H4 * W4;
+    const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x4 = (int)(idx % W4);
+        const int Y = (int)((idx / W4) % H4);
+        const size_t pl = idx / ((size_t)W4 * H4);
+        int xo[4], yo[4];
+        float lx[4], ly[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float fx = sx * (float)(x4 * 4 + k), fy = sy * (float)(Y * 4 + k);
+            xo[k] = (int)fx; lx[k] = fx - (float)xo[k];
+            yo[k] = (int)fy; ly[k] = fy - (float)yo[k];
+        }
+        const int xb = xo[0], yb = yo[0];
+        float src[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float* row = in + (pl * h + min(yb + r, h - 1)) * w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) src[r][c] = __ldg(row + min(xb + c, w - 1));
+        }
+        float hz[3][4];     // horizontally interpolated source rows
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool s1 = xo[k] != xb;        // the 4 outputs span at most two source columns
+                const float a = s1 ? src[r][1] : src[r][0], b = s1 ? src[r][2] : src[r][1];
+                hz[r][k] = (1.f - lx[k]) * a + lx[k] * b;
+            }
+        float* o = out + (pl * H + (size_t)Y * 4) * W + (size_t)x4 * 4;
+#pragma unroll
+        for (int yy = 0; yy < 4; ++yy) {
+            const bool s1 = yo[yy] != yb;
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = s1 ? hz[1][k] : hz[0][k], b = s1 ? hz[2][k] : hz[1][k];
+                v[k] = (1.f - ly[yy]) * a + ly[yy] * b;
+            }
+            *reinterpret_cast<float4*>(o + (size_t)yy * W) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 int upsample_ac_launch(const float* in, float* out, int h, int w, int H, int W, size_t planes, cudaStream_t stream) {
     VPU_REQUIRE(W % 4 == 0, "upsample: output width must be a multiple of 4");
+    if (H % 4 == 0 && H > 1 && W > 1 && 3 * (h - 1) < (H - 1) && 3 * (w - 1) < (W - 1)) {   // 4 outputs within one source step
+        const size_t total = planes * (H / 4) * (W / 4);
+        size_t grid = (total + 255) / 256;
+        if (grid > 148 * 32) grid = 148 * 32;
+        upsample_ac4_kernel<<<(unsigned)grid, 256, 0, stream>>>(in, out, h, w, H, W, planes);
+        VPU_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    }
     const size_t total = planes * H * (W / 4);
     size_t grid = (total + 255) / 256;
     if (grid > 148 * 32) grid = 148 * 32;

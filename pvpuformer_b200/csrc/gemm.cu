@@ -175,7 +175,9 @@ enum EpiKind {
     EK_BF16_RELU = 2,  // out bf16 = relu(acc + bias)                 (FFNs, head convs)
     EK_F32_RES = 3,    // out fp32 = acc + bias + residual fp32       (ViT proj / fc2 on the residual stream)
     EK_GENERIC = 4,    // everything behind run-time flags            (tables, pixel shuffle, bf16 residual ...)
-    EK_HEAD = 5        // EPI_HEAD_FINAL                              (P2CL logits, 1-CTA BN=64 only)
+    EK_HEAD = 5,       // EPI_HEAD_FINAL                              (P2CL logits, 1-CTA BN=64 only)
+    EK_BF16_TAB = 6,   // out bf16 = acc + table[m % rows]            (DMA image-side K|V|Q projection with the folded key_pe)
+    EK_PS = 7          // out bf16 = acc + bias, pixel-shuffle store  (ConvTranspose2d k=2 s=2 of the neck)
 };
 
 constexpr int EPI_PITCH = 36;                        // fp32 words per staged row
@@ -228,9 +230,17 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
         const bool res_bf16 = DYN ? (e.res_bf16 != 0) : false;
         const bool out_bf16 = DYN ? (e.out_bf16 != 0) : (EK != EK_F32_RES);
         const int act = DYN ? e.act : (EK == EK_BF16_GELU ? ACT_GELU : (EK == EK_BF16_RELU ? ACT_RELU : ACT_NONE));
-        const bool has_tab = DYN && e.bias2d != nullptr;
-        const bool pshuf = DYN && e.mode == EPI_PIXEL_SHUFFLE;
+        const bool has_tab = DYN ? (e.bias2d != nullptr) : (EK == EK_BF16_TAB);
+        const bool pshuf = DYN ? (e.mode == EPI_PIXEL_SHUFFLE) : (EK == EK_PS);
         const int sub = lane >> 3, j4 = (lane & 7) * 4;
+        // rows of this lane are r_lo + sub + 4*it: the table row and the pixel-shuffle coordinates are divided out
+        // once per tile and advanced by 4 per step (run-time divisions per row dominated these epilogues before)
+        int trow0 = 0, ps_b0 = 0, ps_i0 = 0, ps_j0 = 0;
+        if (has_tab) trow0 = (r_lo + sub) % e.bias2d_rows;
+        if (pshuf) {
+            const int m0 = r_lo + sub, gg = e.ps_g * e.ps_g, ij = m0 % gg;
+            ps_b0 = m0 / gg; ps_i0 = ij / e.ps_g; ps_j0 = ij % e.ps_g;
+        }
 #pragma unroll 1
         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
             const int n0 = col_base + c;
@@ -271,7 +281,9 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
                     if (has_tab) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias2d + (size_t)(m % e.bias2d_rows) * d.N + n));
+                        int trow = trow0 + 4 * it;                       // table rows >= 32 on this path: at most one wrap
+                        while (trow >= e.bias2d_rows) trow -= e.bias2d_rows;
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias2d + (size_t)trow * d.N + n));
                         v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                     }
                     if (act == ACT_GELU) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
@@ -279,10 +291,12 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                     size_t orow = (size_t)m;
                     int ocol = n;
                     if (pshuf) {
-                        const int g = e.ps_g, gg = g * g;
-                        const int b = m / gg, ij = m % gg, i = ij / g, jx = ij % g;
+                        const int g = e.ps_g;
+                        int jx = ps_j0 + 4 * it, i = ps_i0, b = ps_b0;      // g >= 4 rows per grid line: carries by subtraction
+                        while (jx >= g) { jx -= g; ++i; }
+                        while (i >= g) { i -= g; ++b; }
                         const int q = n / e.ps_cout;
-                        ocol = n % e.ps_cout;
+                        ocol = n - q * e.ps_cout;
                         orow = ((size_t)b * 2 * g + 2 * i + (q >> 1)) * (size_t)(2 * g) + 2 * jx + (q & 1);
                     }
                     if (out_bf16)
@@ -672,6 +686,8 @@ template <int BN> static int attrs2_all() {
     if (int rc = attr2<BN, EK_BF16_GELU>()) return rc;
     if (int rc = attr2<BN, EK_BF16_RELU>()) return rc;
     if (int rc = attr2<BN, EK_F32_RES>()) return rc;
+    if (int rc = attr2<BN, EK_BF16_TAB>()) return rc;
+    if (int rc = attr2<BN, EK_PS>()) return rc;
     return attr2<BN, EK_GENERIC>();
 }
 static int set_smem_attrs() {
@@ -764,6 +780,8 @@ static int launch_tc2_k(const GemmProblem& p, cudaStream_t stream) {
 
 // pick the compile-time epilogue the problem's run-time flags describe
 static int epi_kind(const Epi& e) {
+    if (e.mode == EPI_PIXEL_SHUFFLE && e.out_bf16 && !e.res && !e.bias2d && e.act == ACT_NONE && e.ps_g >= 8) return EK_PS;
+    if (e.mode == EPI_PLAIN && e.bias2d && e.bias2d_rows >= 32 && e.out_bf16 && !e.res && e.act == ACT_NONE) return EK_BF16_TAB;
     if (e.mode != EPI_PLAIN || e.bias2d) return EK_GENERIC;
     if (e.out_bf16 && !e.res) return e.act == ACT_GELU ? EK_BF16_GELU : (e.act == ACT_RELU ? EK_BF16_RELU : EK_BF16);
     if (!e.out_bf16 && e.res && !e.res_bf16 && e.act == ACT_NONE) return EK_F32_RES;
@@ -777,6 +795,8 @@ static int launch_tc2(const GemmProblem& p, cudaStream_t stream) {
         case EK_BF16_GELU: return launch_tc2_k<BN, EK_BF16_GELU>(p, stream);
         case EK_BF16_RELU: return launch_tc2_k<BN, EK_BF16_RELU>(p, stream);
         case EK_F32_RES: return launch_tc2_k<BN, EK_F32_RES>(p, stream);
+        case EK_BF16_TAB: return launch_tc2_k<BN, EK_BF16_TAB>(p, stream);
+        case EK_PS: return launch_tc2_k<BN, EK_PS>(p, stream);
         default: return launch_tc2_k<BN, EK_GENERIC>(p, stream);
     }
 }
