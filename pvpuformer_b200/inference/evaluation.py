@@ -1,0 +1,201 @@
+"""NoC evaluation loop (reference isegm/inference/vpu_evaluation.py:18-98, metrics of inference/utils.py:80-110)
+plus what the reference does not have: lock-step batched evaluation and sharding over ranks.
+
+The click loop is sequential only WITHIN an image (the next click depends on the last mask); images and click
+sessions are independent (nothing in the forward mixes batch elements).  `evaluate_lockstep` therefore advances
+many sessions one click at a time and feeds all of them to ONE network call (model batch = 2 x sessions with flip
+TTA), and `evaluate_sharded` gives every rank a contiguous block of images, with no collective in the loop and a
+single all_gather of the per-image IoU table at the end (NCCL on GPUs, gloo in the CPU tests).
+"""
+from time import time
+
+import numpy as np
+import torch
+
+from .clicker import Clicker
+from .predictor import vpu_eval_predictor
+
+
+def get_iou(gt_mask, pred_mask, ignore_label=-1):
+    keep = gt_mask != ignore_label
+    obj = gt_mask == 1
+    inter = np.logical_and(np.logical_and(pred_mask, obj), keep).sum()
+    union = np.logical_and(np.logical_or(pred_mask, obj), keep).sum()
+    return inter / union
+
+
+def compute_noc_metric(all_ious, iou_thrs, max_clicks=20):
+    """-> (mean NoC, std NoC, number of objects that needed max_clicks) per IoU threshold."""
+    noc_list, noc_std, over_max = [], [], []
+    for thr in iou_thrs:
+        scores = []
+        for ious in all_ious:
+            hit = np.asarray(ious) >= thr
+            scores.append(int(np.argmax(hit)) + 1 if hit.any() else max_clicks)
+        scores = np.array(scores, dtype=np.int64)
+        noc_list.append(scores.mean())
+        noc_std.append(scores.std())
+        over_max.append(int((scores == max_clicks).sum()))
+    return noc_list, noc_std, over_max
+
+
+def evaluate_sample(image, gt_mask, predictor, max_iou_thr, pred_thr=0.49, min_clicks=1, max_clicks=20, sample_id=None,
+                    callback=None, as_prompt_type=0):
+    clicker = Clicker(gt_mask=gt_mask)
+    pred_mask = np.zeros_like(gt_mask)
+    ious = []
+    pred_probs = None
+    with torch.no_grad():
+        predictor.set_input_image(image)
+        for click_indx in range(max_clicks):
+            clicker.make_next_click(pred_mask)
+            pred_probs, prompts = predictor.get_vqu_prediction(clicker, gt_mask=gt_mask, as_prompt_type=as_prompt_type,
+                                                               click_indx=click_indx, as_multi_prompts=True)
+            pred_mask = pred_probs > pred_thr
+            iou = get_iou(gt_mask, pred_mask)
+            ious.append(iou)
+            done = iou >= max_iou_thr and click_indx + 1 >= min_clicks
+            if callback is not None:
+                callback(image, gt_mask, pred_probs, iou, sample_id, click_indx, clicker.clicks_list, done,
+                         predictor.zoom_in, prompts, as_prompt_type)
+            if done:
+                break
+    return clicker.clicks_list, np.array(ious, dtype=np.float32), pred_probs
+
+
+def evaluate_dataset(dataset, predictor, **kwargs):
+    all_ious = []
+    t0 = time()
+    for index in range(len(dataset)):
+        sample = dataset.get_sample(index)
+        for object_id in sample.objects_ids:
+            _, ious, _ = evaluate_sample(sample.image, sample.gt_mask(object_id), predictor, sample_id=index, **kwargs)
+            all_ious.append(ious)
+    return all_ious, time() - t0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lock-step batched evaluation
+# ---------------------------------------------------------------------------------------------------------
+def _repack_points(points_nd, n):
+    """[r, 2k, 3] -> [r, 2n, 3]: each half padded with (-1,-1,-1) rows (the network pads to num_max_points anyway)."""
+    k = points_nd.shape[1] // 2
+    if k == n:
+        return points_nd
+    pad = points_nd.new_full((points_nd.shape[0], n - k, 3), -1)
+    return torch.cat([points_nd[:, :k], pad, points_nd[:, k:], pad], dim=1)
+
+
+def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clicks=1, max_clicks=20, micro_batch=32,
+                      predictor_factory=vpu_eval_predictor, stats=None):
+    """samples: list of (image HWC, gt_mask HW).  Returns the list of per-sample IoU arrays, identical to running
+    evaluate_sample on each (the forward is batch-independent), but with ONE network call per click per micro-batch.
+    `stats` (dict, optional) receives the number of network calls and click-forwards executed."""
+    results = [None] * len(samples)
+    n_calls = n_fwd = 0
+    with torch.no_grad():
+        for lo in range(0, len(samples), micro_batch):
+            chunk = list(range(lo, min(lo + micro_batch, len(samples))))
+            sess = {}
+            for i in chunk:
+                image, gt = samples[i]
+                p = predictor_factory(net, device)
+                if p.cascade_step > 1:
+                    raise NotImplementedError("lock-step evaluation supports cascade_step <= 1")
+                p.set_input_image(image)
+                sess[i] = dict(pred=p, clicker=Clicker(gt_mask=gt), gt=gt, mask=np.zeros_like(gt), ious=[])
+            active = list(chunk)
+            for click_indx in range(max_clicks):
+                if not active:
+                    break
+                prepared = []
+                for i in active:
+                    s = sess[i]
+                    s["clicker"].make_next_click(s["mask"])
+                    image_nd, points_nd, _ = s["pred"].prepare_inputs(s["clicker"], None, s["gt"], 0)
+                    prepared.append((image_nd, points_nd))
+                n = max(p.shape[1] // 2 for _, p in prepared)
+                images = torch.cat([im for im, _ in prepared], dim=0)
+                points = torch.cat([_repack_points(p.to(torch.float64), n) for _, p in prepared], dim=0)
+                logits = net(images, points)["instances"]
+                n_calls += 1
+                n_fwd += images.shape[0]
+                still, row = [], 0
+                for i, (image_nd, _) in zip(active, prepared):
+                    s = sess[i]
+                    r = image_nd.shape[0]
+                    pred = s["pred"].finish_prediction(logits[row:row + r], image_nd.shape[2:])
+                    row += r
+                    s["pred"].prev_prediction = pred
+                    probs = pred.cpu().numpy()[0, 0]
+                    s["mask"] = probs > pred_thr
+                    iou = get_iou(s["gt"], s["mask"])
+                    s["ious"].append(iou)
+                    if not (iou >= max_iou_thr and click_indx + 1 >= min_clicks):
+                        still.append(i)
+                active = still
+            for i in chunk:
+                results[i] = np.array(sess[i]["ious"], dtype=np.float32)
+    if stats is not None:
+        stats["network_calls"] = stats.get("network_calls", 0) + n_calls
+        stats["click_forwards"] = stats.get("click_forwards", 0) + n_fwd
+    return results
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sharding over ranks
+# ---------------------------------------------------------------------------------------------------------
+def shard_range(n, rank, world):
+    """Contiguous block of rank `rank`: [start, stop); sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def iou_table(all_ious, max_clicks):
+    """list of variable-length IoU arrays -> [n, max_clicks] fp32, NaN after an early stop."""
+    t = np.full((len(all_ious), max_clicks), np.nan, dtype=np.float32)
+    for i, ious in enumerate(all_ious):
+        t[i, :len(ious)] = ious
+    return t
+
+
+def gather_iou_tables(local_table, n_total, group=None, device=None):
+    """all_gather of the per-rank [n_local, max_clicks] tables -> [n_total, max_clicks] on every rank (rank order ==
+    image order because shards are contiguous).  The only collective of the sharded NoC loop."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_table
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    max_clicks = local_table.shape[1]
+    cap = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    buf = torch.full((cap, max_clicks), float("nan"), dtype=torch.float32)
+    buf[:local_table.shape[0]] = torch.from_numpy(local_table)
+    if device is not None:
+        buf = buf.to(device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    parts = []
+    for r in range(world):
+        a, b = shard_range(n_total, r, world)
+        parts.append(out[r][:b - a].cpu().numpy())
+    return np.concatenate(parts, axis=0)
+
+
+def evaluate_sharded(dataset, net, device, rank, world, max_iou_thr, max_clicks=20, micro_batch=32, group=None,
+                     gather_device=None, **kwargs):
+    """Rank `rank` evaluates images [start, stop) in lock-step micro-batches; returns the full [n, max_clicks] IoU
+    table (after the all_gather) and the local wall-clock seconds of the loop."""
+    start, stop = shard_range(len(dataset), rank, world)
+    samples = []
+    for index in range(start, stop):
+        s = dataset.get_sample(index)
+        for object_id in s.objects_ids:
+            samples.append((s.image, s.gt_mask(object_id)))
+    t0 = time()
+    stats = {}
+    ious = evaluate_lockstep(samples, net, device, max_iou_thr, max_clicks=max_clicks, micro_batch=micro_batch, stats=stats,
+                             **kwargs)
+    elapsed = time() - t0
+    table = gather_iou_tables(iou_table(ious, max_clicks), len(dataset), group=group, device=gather_device)
+    return table, elapsed, stats

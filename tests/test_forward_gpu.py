@@ -154,3 +154,25 @@ def test_error_behaviour():
         m(torch.zeros(1, 4, 448, 448).cuda(), torch.full((1, 50, 3), -1.0).cuda())   # n > 24 unsupported (reference too)
     with pytest.raises(ValueError):
         m(torch.zeros(1, 4, 448, 448).cuda(), torch.zeros(1, 2, 3).cuda(), None, 1)  # box prompts missing
+
+
+def test_noc_lockstep_on_gpu_matches_serial_predictor():
+    """NoBRS plumbing on the CUDA model: the lock-step batched NoC loop (one network call per click for all sessions,
+    batch = 2 x sessions with flip TTA) reproduces the serial per-image loop bit for bit, ZoomIn crops included."""
+    from pvpuformer_b200.inference import evaluate_lockstep, evaluate_sample
+    from pvpuformer_b200.inference.datasets import SyntheticEllipseDataset
+    from pvpuformer_b200.inference.predictor import vpu_eval_predictor
+    m, _ = _model("vit_base")
+    dev = torch.device("cuda:0")
+    ds = SyntheticEllipseDataset(3, seed0=40)
+    samples = [(ds.get_sample(i).image, ds.get_sample(i).gt_mask(1)) for i in range(3)]
+    m.want_aux = False
+    try:
+        serial = [evaluate_sample(im, gt, vpu_eval_predictor(m, dev), 1.01, max_clicks=3)[1] for im, gt in samples]
+        stats = {}
+        lock = evaluate_lockstep(samples, m, dev, 1.01, max_clicks=3, micro_batch=3, stats=stats)
+    finally:
+        m.want_aux = True
+    for a, b in zip(serial, lock):
+        assert len(a) == 3 and np.array_equal(a, b)
+    assert stats == {"network_calls": 3, "click_forwards": 18}
