@@ -35,7 +35,7 @@ GFLOP_PER_CLICK_FORWARD = {"vit_base": 170.7, "vit_large": 538.7, "vit_huge": 14
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arch", default="vit_base", choices=["vit_base", "vit_large", "vit_huge"])
@@ -120,42 +120,63 @@ def run_reference(args, rank):
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi polled every 20 ms from before the warm-up; only samples stamped inside the timed window count."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
+    def begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.p.terminate()
         try:
             out, _ = self.p.communicate(timeout=5)
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], None, set()
+        sm, pw, mx, reasons, total = [], [], None, set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                clk, mxc = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for nme, v in zip(names, f[3:7]):
+            total += 1
+            if self.t0 is not None and not (self.t0 <= ts <= self.t1):
+                continue
+            sm.append(clk)
+            mx = mxc
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
+            for nme, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "samples_total": total,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
 def profile_classes(model, L, steps, run_step):
@@ -216,27 +237,36 @@ def main():
     def step_resident():
         return model(image_d, points_d)
 
-    out_h = torch.empty(B, 1, cfg.img_size, cfg.img_size, dtype=torch.float32).pin_memory()
+    out_h = torch.empty(B, 1, cfg.img_size, cfg.img_size, dtype=torch.float32)      # shape of the per-step D2H result
+
+    from pvpuformer_b200.pipeline import HostPipeline
+    pipe = HostPipeline(model, dev, depth=3)
 
     def step_e2e():
-        img = image_h.to(dev, non_blocking=True)
-        pts = points_h.to(dev, non_blocking=True)
-        o = model(img, pts)
-        out_h.copy_(o["instances"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the result of every step
+        # every step: H2D of this step's image + click tensors (pinned), forward, D2H of 'instances' into pinned host
+        # memory; the pipeline keeps up to 3 steps in flight so the copies of neighbouring steps overlap the forward
+        pipe.submit(image_h, points_h)
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, drain=None):
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         for _ in range(warmup):
             fn()
+        if drain:
+            drain()
         barrier()
-        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.begin()
         l0 = lib.vpu_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if drain:
+            drain()                                    # every step's result has landed on the host
         e1.record()
         barrier()
+        if sampler:
+            sampler.end()
         launches = lib.vpu_launch_count() - l0
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
@@ -250,11 +280,12 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
     e2e = None
     if not args.no_e2e:
-        ms_e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+        ms_e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3), drain=pipe.drain)
         e2e = {"value": world * B * args.steps / (ms_e * 1e-3), "unit": METRIC,
                "h2d_bytes_per_step": image_h.numel() * 4 + points_h.numel() * 8, "d2h_bytes_per_step": out_h.numel() * 4,
                "ms_per_step": ms_e / args.steps,
-               "call": "VitMultiGaussianVector_ed_Model.forward(image, points) with pinned host tensors; D2H of 'instances'"}
+               "call": "pipeline.HostPipeline(model).submit(image, points): pinned host tensors -> H2D -> "
+                       "VitMultiGaussianVector_ed_Model.forward -> D2H of 'instances' into pinned host memory, 3 steps in flight"}
 
     classes = profile_classes(model, L, args.profile_steps, step_resident) if (rank == 0 and args.profile_steps > 0) else []
     if world > 1:
