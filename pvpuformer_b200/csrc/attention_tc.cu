@@ -79,6 +79,11 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU; arguments are <= 0 here, results in (0, 1]
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // MN-major 128B-swizzled operand (V: rows = keys (K), 64 head-dim elements = one 128-byte row):
@@ -233,58 +238,74 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
         const int row = quarter * 32 + lane;             // query row inside the tile
         const int nvalid = t == 0 ? T0_ROWS : T1_ROWS;
         const uint32_t tile_tmem = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * TILE_COLS;
+        const bool warp_has_rows = quarter * 32 < nvalid;
         uint32_t tphase = 0;
         for (int p = blockIdx.x; p < a.nprob; p += gridDim.x) {
             const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
             mbar_wait(&s_full[t], tphase);
             tc_fence_after();
-            // pass 1: row maximum over the 196 valid keys
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 6; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tile_tmem + c * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-            }
-            {
-                uint32_t r[16];
-                tmem_ld_32x16(tile_tmem + 192, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < SK - 192; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-            }
-            const float moff = mx * a.scale_log2;
-            // pass 2: p = exp2(s * scale - max * scale), bf16 pairs written over the already-consumed S columns
             float sum = 0.f;
+            if (warp_has_rows) {      // warps whose 32 rows are all past the tile's valid queries only keep the barriers moving
+                // pass 1: row maximum over the 196 valid keys; the TMEM load of chunk c+1 is in flight while chunk c is reduced
+                float mx = -INFINITY;
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32(tile_tmem, ra);
 #pragma unroll 1
-            for (int c = 0; c < 6; ++c) {
-                uint32_t r[32], pk[16];
-                tmem_ld_32x32(tile_tmem + c * 32, r);
+                for (int c = 0; c < 6; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tile_tmem + (c + 1) * 32, rb);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
+                    tmem_ld_wait();
+                    if (c + 2 < 6) tmem_ld_32x32(tile_tmem + (c + 2) * 32, ra);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
+                }
+                uint32_t rt[16];
+                tmem_ld_32x16(tile_tmem + 192, rt);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float p0 = exp2f(fmaf(__uint_as_float(r[2 * i]), a.scale_log2, -moff));
-                    const float p1 = exp2f(fmaf(__uint_as_float(r[2 * i + 1]), a.scale_log2, -moff));
-                    sum += p0 + p1;
-                    pk[i] = pack_bf16(p0, p1);
-                }
-                tmem_st_32x16(tile_tmem + c * 16, pk);
-            }
-            {
-                uint32_t r[16], pk[8];
-                tmem_ld_32x16(tile_tmem + 192, r);
-                tmem_ld_wait();
+                for (int i = 0; i < SK - 192; ++i) mx = fmaxf(mx, __uint_as_float(rt[i]));
+                const float moff = mx * a.scale_log2;
+                // pass 2: p = exp2(s * scale - max * scale), bf16 pairs written over the already-consumed S columns
+                auto expo = [&](uint32_t sbits) { return ex2_approx(fmaf(__uint_as_float(sbits), a.scale_log2, -moff)); };
+                tmem_ld_32x32(tile_tmem, ra);
+#pragma unroll 1
+                for (int c = 0; c < 6; c += 2) {
+                    uint32_t pk[16];
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tile_tmem + (c + 1) * 32, rb);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float p0 = 0.f, p1 = 0.f;
-                    if (2 * i < SK - 192) p0 = exp2f(fmaf(__uint_as_float(r[2 * i]), a.scale_log2, -moff));
-                    if (2 * i + 1 < SK - 192) p1 = exp2f(fmaf(__uint_as_float(r[2 * i + 1]), a.scale_log2, -moff));
-                    sum += p0 + p1;
-                    pk[i] = pack_bf16(p0, p1);
+                    for (int i = 0; i < 16; ++i) {
+                        const float p0 = expo(ra[2 * i]), p1 = expo(ra[2 * i + 1]);
+                        sum += p0 + p1;
+                        pk[i] = pack_bf16(p0, p1);
+                    }
+                    tmem_st_32x16(tile_tmem + c * 16, pk);
+                    tmem_ld_wait();
+                    if (c + 2 < 6) tmem_ld_32x32(tile_tmem + (c + 2) * 32, ra);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float p0 = expo(rb[2 * i]), p1 = expo(rb[2 * i + 1]);
+                        sum += p0 + p1;
+                        pk[i] = pack_bf16(p0, p1);
+                    }
+                    tmem_st_32x16(tile_tmem + (c + 1) * 16, pk);
                 }
-                tmem_st_32x8(tile_tmem + 96, pk);
+                {
+                    uint32_t pk[8];
+                    tmem_ld_32x16(tile_tmem + 192, rt);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float p0 = 0.f, p1 = 0.f;
+                        if (2 * i < SK - 192) p0 = expo(rt[2 * i]);
+                        if (2 * i + 1 < SK - 192) p1 = expo(rt[2 * i + 1]);
+                        sum += p0 + p1;
+                        pk[i] = pack_bf16(p0, p1);
+                    }
+                    tmem_st_32x8(tile_tmem + 96, pk);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -293,7 +314,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             // epilogue: O / rowsum -> bf16 -> token-major output row of this query
             mbar_wait(&o_full[t], tphase);
             tc_fence_after();
-            const float inv = 1.0f / sum;
+            const float inv = warp_has_rows ? 1.0f / sum : 0.f;
             const int wi = w / a.nwin_side, wj = w % a.nwin_side;
             const int s = (t == 0 ? 0 : T0_ROWS) + row, i = s / WIN, j = s % WIN;
             __nv_bfloat16* dst = a.o + ((size_t)b * a.tokens + (size_t)(wi * WIN + i) * a.grid + wj * WIN + j) * a.ldo + h * D;

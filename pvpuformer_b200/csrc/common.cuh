@@ -169,6 +169,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+// same, multicast: the box lands at this shared-memory offset in every CTA of `mask`, each destination's pair leader is signalled
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* tm, uint64_t* leader_bar, int c0, int c1,
+                                                   uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1),
+        "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the leader CTA's barrier
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }

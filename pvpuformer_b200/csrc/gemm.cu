@@ -463,8 +463,8 @@ template <int BN> struct TileCfg2 {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024;
 };
 
-template <int BN, int EK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EK, int CL>   // CL = CTAs per cluster: 2 (one MMA pair) or 4 (two pairs sharing the B tile by TMA multicast)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDims d,
                 const Epi e) {
     using C = TileCfg2<BN>;
@@ -475,7 +475,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    constexpr int PP = CL / 2;                        // MMA pairs per cluster (stacked along M, same N tile)
+    const uint32_t crank = cluster_ctarank();
+    const int rank = (int)(crank & 1);                // position inside the MMA pair
+    const int pr = (int)(crank >> 1);                 // pair inside the cluster
     const bool leader = rank == 0;
 
     if (warp == 0 && lane == 0) {
@@ -483,7 +486,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], PP);   // one multicast commit per pair that reads (and whose peers write) this stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
@@ -501,10 +504,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = tmem_base_smem;
 
     const int n_blks = (d.N + BN - 1) / BN;
-    const int m_blks = (d.M + 2 * BM - 1) / (2 * BM);
+    const int m_blks = (d.M + 2 * BM * PP - 1) / (2 * BM * PP);     // cluster tiles along M: PP * 256 rows each
     const int tiles = n_blks * m_blks;
     const int kblks = (d.K + BK - 1) / BK;
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int pair = blockIdx.x / CL, npairs = gridDim.x / CL;      // cluster index / number of clusters
+    constexpr uint16_t kAllMask = (uint16_t)((1u << CL) - 1);
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));
     const int nst = d.stages > 0 && d.stages < C::STAGES ? d.stages : C::STAGES;
 
     if (warp == 0) {
@@ -513,8 +518,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t phase = 0;
             for (int tile = pair; tile < tiles; tile += npairs) {
                 const int m_blk = tile / n_blks, n_blk = tile % n_blks;
-                const int arow = m_blk * 2 * BM + (int)rank * BM;
-                const int brow = n_blk * BN + (int)rank * (BN / 2);
+                const int arow = (m_blk * PP + pr) * 2 * BM + rank * BM;
+                // this CTA fetches 1/PP of the B half its pair position needs and multicasts it to the CTAs at the same
+                // position in every pair of the cluster
+                const int brow = n_blk * BN + rank * (BN / 2) + pr * (BN / 2 / PP);
+                const uint16_t bmask = (uint16_t)(PP == 1 ? 0 : ((1u << rank) | (1u << (2 + rank))));
                 for (int kb = 0; kb < kblks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (d.ablate & 1) {
@@ -523,7 +531,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
                         uint8_t* sa = smem + stage * C::STAGE_BYTES;
                         tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, arow);
-                        tma_load_2d_2sm(sa + C::A_BYTES, &tmB, &full_bar[stage], kb * BK, brow);
+                        if constexpr (PP == 1)
+                            tma_load_2d_2sm(sa + C::A_BYTES, &tmB, &full_bar[stage], kb * BK, brow);
+                        else
+                            tma_load_2d_2sm_mc(sa + C::A_BYTES + pr * (C::B_BYTES / PP), &tmB, &full_bar[stage], kb * BK, brow, bmask);
                     }
                     if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
@@ -551,10 +562,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
                                       idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit_2sm(&empty_bar[stage], 3);   // frees this stage in BOTH CTAs
+                    umma_commit_2sm(&empty_bar[stage], kAllMask);   // this pair is done with the stage: tell every CTA that writes into it
                     if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2sm(&tfull_bar[acc], 3);         // accumulator halves complete in both CTAs
+                umma_commit_2sm(&tfull_bar[acc], pair_mask); // accumulator halves complete in both CTAs of this pair
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -568,7 +579,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int m_blk = tile / n_blks, n_blk = tile % n_blks;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, m_blk * 2 * BM + (int)rank * BM, n_blk * BN, quarter, half,
+            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, (m_blk * PP + pr) * 2 * BM + rank * BM, n_blk * BN, quarter, half,
                               lane, reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES) + (warp - 2) * EPI_WARP_WORDS);
             tc_fence_before();
             __syncwarp();
@@ -653,6 +664,7 @@ static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
 static bool g_use_2cta = true;
 static int g_stages = 0;
+static int g_cluster = 2;
 static int g_ablate = 0;
 static std::mutex g_mu;
 
@@ -678,7 +690,8 @@ template <int BN, int EK> static int attr1() {
     return 0;
 }
 template <int BN, int EK> static int attr2() {
-    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg2<BN>::SMEM_BYTES));
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg2<BN>::SMEM_BYTES));
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg2<BN>::SMEM_BYTES));
     return 0;
 }
 template <int BN> static int attrs2_all() {
@@ -718,6 +731,7 @@ int gemm_init() {
     const char* two = getenv("VPU_GEMM_2CTA");
     g_use_2cta = !(two && two[0] == '0');
     if (const char* st = getenv("VPU_GEMM_STAGES")) g_stages = atoi(st);
+    if (const char* cl = getenv("VPU_GEMM_CLUSTER")) g_cluster = atoi(cl) == 4 ? 4 : 2;
     if (const char* ab = getenv("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
@@ -763,19 +777,39 @@ static int launch_tc(const GemmProblem& p, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, int EK>
-static int launch_tc2_k(const GemmProblem& p, cudaStream_t stream) {
+template <int BN, int EK, int CL>
+static int launch_tc2_cl(const GemmProblem& p, cudaStream_t stream) {
+    constexpr int PP = CL / 2;
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap(&tmA, p.A, p.M, p.K, p.lda, BM)) return rc;
-    if (int rc = make_tmap(&tmB, p.W, p.w_rows ? p.w_rows : p.N, p.K, p.ldw, BN / 2)) return rc;
-    const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
-    const int max_pairs = g_num_sms / 2;
-    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    if (int rc = make_tmap(&tmB, p.W, p.w_rows ? p.w_rows : p.N, p.K, p.ldw, BN / 2 / PP)) return rc;
+    const int tiles = ((p.M + 2 * BM * PP - 1) / (2 * BM * PP)) * ((p.N + BN - 1) / BN);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = TileCfg2<BN>::SMEM_BYTES; cfg.stream = stream;
+    static int max_clusters = 0;      // co-resident clusters of this instantiation (a persistent grid must not exceed it by much)
+    if (max_clusters == 0) {
+        cfg.gridDim = dim3(CL * (g_num_sms / CL));
+        int n = 0;
+        VPU_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<BN, EK, CL>, &cfg));
+        max_clusters = n > 0 ? n : 1;
+    }
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    cfg.gridDim = dim3(CL * clusters);
     GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
-    gemm_tc2_kernel<BN, EK><<<2 * pairs, GEMM_THREADS, TileCfg2<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d, p.epi);
-    VPU_CHECK_CUDA(cudaGetLastError());
+    VPU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN, EK, CL>, tmA, tmB, d, p.epi));
     count_launch();
     return 0;
+}
+
+template <int BN, int EK>
+static int launch_tc2_k(const GemmProblem& p, cudaStream_t stream) {
+    // clusters of 4 (B-tile multicast between two MMA pairs) need at least two 256-row blocks along M
+    if (g_cluster == 4 && p.M >= 4 * BM) return launch_tc2_cl<BN, EK, 4>(p, stream);
+    return launch_tc2_cl<BN, EK, 2>(p, stream);
 }
 
 // pick the compile-time epilogue the problem's run-time flags describe
