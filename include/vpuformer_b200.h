@@ -118,6 +118,9 @@ int vpu_gemm_pixel_shuffle(const void* A_bf16, const void* W_bf16, int M, int co
 int vpu_attention(const void* q, int ldq, int qoff, const void* k, int ldk, int koff, const void* v, int ldv, int voff,
                   void* o, int ldo, int Sq, int Sk, int heads, int head_dim, int nprob, float scale, int window,
                   int grid, void* stream);
+/* measurement only: CTA 0 of the following global-attention launches logs (event << 56 | clock64) per role into
+ * dev_buf[4][cap] (uint64; roles: TMA thread, MMA thread, softmax warpgroup 0 / 1); NULL switches it off */
+int vpu_debug_attention_trace(void* dev_buf, int cap);
 int vpu_layernorm(const float* in, const float* gamma, const float* beta, float eps, int rows, int C, float* out_f32,
                   void* out_bf16, const float* pe, void* out_pe_bf16, float* rowmax, void* stream);
 int vpu_groupnorm_nhwc(void* x_bf16, int B, int64_t per_sample, int C, const float* gamma, const float* beta, int gelu,

@@ -772,6 +772,11 @@ int vpu_attention(const void* q, int ldq, int qoff, const void* k, int ldk, int 
     return attention_launch(a, head_dim, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int vpu_debug_attention_trace(void* dev_buf, int cap) {
+    attention_debug_trace(reinterpret_cast<unsigned long long*>(dev_buf), dev_buf ? cap : 0);
+    return 0;
+}
+
 int vpu_layernorm(const float* in, const float* gamma, const float* beta, float eps, int rows, int C, float* out_f32,
                   void* out_bf16, const float* pe, void* out_pe_bf16, float* rowmax, void* stream) {
     VPU_REQUIRE(in && gamma && beta, "vpu_layernorm: null argument");

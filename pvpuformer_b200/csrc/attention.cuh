@@ -31,5 +31,10 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream);
 // tcgen05 / TMEM kernel for 14x14-token windows, head_dim 64 (attention_tc.cu)
 bool window_attention_tc_supported(const AttnArgs& a, int head_dim);
 int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
+// tcgen05 / TMEM flash kernel for un-windowed self-attention, head_dim 64, S a multiple of 112 (attention_tc.cu)
+bool global_attention_tc_supported(const AttnArgs& a, int head_dim);
+int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
+// measurement only: CTA 0 of the next global-attention launches logs (event << 56 | clock64) into dev_buf[4 roles][cap]
+void attention_debug_trace(unsigned long long* dev_buf, int cap);
 
 }  // namespace vpu

@@ -14,6 +14,7 @@
 // Scores and probabilities never touch shared or global memory.  The MMA warp software-pipelines
 // S(n+1) between the two P V products of problem n, and Q/K/V of the next problem are prefetched into
 // the second shared-memory stage while the current one is in flight.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -83,6 +84,11 @@ __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU; arguments 
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -349,6 +355,389 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
     }
 }
 
+// =====================================================================================================
+// Global (un-windowed) self-attention of the ViT blocks 6 / 12 (/ 18 / 24): S = 784 tokens, head_dim 64
+// (reference models_vit.py:43-56 on the full token sequence, models_vit.py:274-286).
+//
+// Flash-style: the 784 x 784 score matrix never exists; a CTA owns two 128-query tiles of one (image, head)
+// and streams the keys / values in 7 blocks of 112 (784 = 7 x 112: no key masking anywhere).
+//   work unit   (image, head, query-tile pair); 7 query tiles per problem -> 4 pairs, the last holds one tile
+//   per block j S_t = Q_t K_j^T     tcgen05.mma M=128 N=112 K=64, fp32 in TMEM columns [0,112) of tile t
+//               P_t = exp2(S_t - m) softmax warpgroup t (thread == query row) -> bf16 in TMEM columns [112,168)
+//               O_t += P_t V_j      tcgen05.mma, A operand from TMEM, V MN-major from shared memory, O in [192,256)
+// Online softmax with the lazy rescale of FlashAttention-4: the running maximum m is only raised (and O, l
+// rescaled in TMEM) when a block's maximum exceeds it by more than 2^8, which is exact -- the final O / l is
+// independent of m -- and makes the correction a rare warp-uniform branch instead of a per-block O round trip.
+// The softmax warpgroup pulls a whole S row block into registers and releases the S columns at once, so the
+// MMA warp computes S(j+1) under the exponentials of block j (a warpgroup never waits for the tensor pipe in
+// steady state; the kernel is bound by the 16 ex2/clk/SM of the MUFU pipe, not by the MMAs), and the two
+// query tiles of the CTA keep that pipe busy from two independent chains.
+// =====================================================================================================
+constexpr int G_KB = 112;                            // keys per block
+constexpr int G_QT = 128;                            // query rows per tile
+constexpr int G_Q_BYTES = G_QT * D * 2;              // 16 KB
+constexpr int G_KV_BYTES = G_KB * D * 2;             // 14 KB
+constexpr int G_STAGE_BYTES = 2 * G_KV_BYTES;        // K block + V block
+constexpr int G_STAGES = 4;
+constexpr int G_SMEM_BYTES = 2 * 2 * G_Q_BYTES + G_STAGES * G_STAGE_BYTES + 1024;
+constexpr int G_P_COL = 112, G_O_COL = 192;
+constexpr int G_MMA1_WARP = 10;                      // warp 0 TMA, 1 MMA tile 0, 2-5 / 6-9 softmax tile 0 / 1, 10 MMA tile 1
+constexpr int G_THREADS = 352;
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+        "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+struct GlobArgs {
+    __nv_bfloat16* o;
+    int ldo;
+    int heads, S;                 // tokens per problem (multiple of 112)
+    int nblocks;                  // S / 112
+    int ntiles, npairs;           // query tiles per problem, tile pairs per problem
+    int nunits;                   // problems * heads * npairs
+    int qcol, kcol, vcol;
+    float scale_log2;
+    int ablate;                   // measurement only (VPU_ATTN_ABLATE): 1 = no ex2, 2 = no PV MMAs, 4 = no S MMAs; results are garbage
+    unsigned long long* trace;    // measurement only (vpu_debug_attention_trace): CTA 0 logs (event << 56 | clock) per role
+    int trace_cap;
+};
+
+// Measurement hooks (clock64 trace of CTA 0, ablation of the exponentials / MMAs) are compiled in only with
+// -DVPU_ATTN_DEBUG: a lone warp retires one dependent instruction per ~10 clk, so even untaken checks cost time here.
+#ifdef VPU_ATTN_DEBUG
+#define G_TRACE(role, code)                                                                              \
+    do {                                                                                                 \
+        if (a.trace && blockIdx.x == 0 && tr_n < a.trace_cap)                                            \
+            a.trace[(role) * a.trace_cap + tr_n++] = ((unsigned long long)(code) << 56) | (clock64() & 0xFFFFFFFFFFFFFFull); \
+    } while (0)
+#define G_ABLATE(bit) (a.ablate & (bit))
+#else
+#define G_TRACE(role, code) do { } while (0)
+#define G_ABLATE(bit) 0
+#endif
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+global_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const GlobArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t q_full[2], q_empty[2], kv_full[G_STAGES], kv_empty[G_STAGES], s_full[2], s_free[2], p_full[2], pv_done[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t KV_OFF = 4 * G_Q_BYTES;       // after the two double-buffered Q tile pairs
+    int tr_n = 0;
+    (void)tr_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 2);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 4);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&pv_done[i], 1);
+        }
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 2);     // one commit per MMA warp (tile)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int last_tile_pair = a.npairs - 1;
+    const bool odd_tiles = (a.ntiles & 1) != 0;      // the last pair of every problem holds a single tile
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- TMA producer ----------------
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int u = blockIdx.x; u < a.nunits; u += gridDim.x, ++it) {
+                const int pr = u % a.npairs, bh = u / a.npairs, h = bh % a.heads, b = bh / a.heads;
+                const bool two = !(odd_tiles && pr == last_tile_pair);
+                const int qb = it & 1;
+                mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&q_full[qb], (two ? 2 : 1) * G_Q_BYTES);
+                uint8_t* qs = smem + qb * 2 * G_Q_BYTES;
+                tma_load_2d(qs, &tmQ, &q_full[qb], a.qcol + h * D, b * a.S + (2 * pr) * G_QT);
+                if (two) tma_load_2d(qs + G_Q_BYTES, &tmQ, &q_full[qb], a.qcol + h * D, b * a.S + (2 * pr + 1) * G_QT);
+                for (int j = 0; j < a.nblocks; ++j) {
+                    mbar_wait(&kv_empty[stage], phase ^ 1);
+                    G_TRACE(0, 1);
+                    mbar_arrive_expect_tx(&kv_full[stage], G_STAGE_BYTES);
+                    uint8_t* st = smem + KV_OFF + stage * G_STAGE_BYTES;
+                    tma_load_2d(st, &tmK, &kv_full[stage], a.kcol + h * D, b * a.S + j * G_KB);
+                    tma_load_2d(st + G_KV_BYTES, &tmV, &kv_full[stage], a.vcol + h * D, b * a.S + j * G_KB);
+                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == G_MMA1_WARP) {
+        // ---------------- MMA issuers: one warp per query tile ----------------
+        // A lone warp retires a dependent instruction every ~10 clk, so everything this role executes per key block
+        // sits on the kernel's critical path (clock64 trace, tools/attn_trace.py: one warp issuing both tiles' 22 MMAs
+        // through `if (lane == 0)` -- where nvcc wraps every tcgen05.mma in an elect / BRA.U.ANY loop and rebuilds the
+        // descriptors on the uniform datapath -- needed 3500 clk per block, twice the exponentials).  Hence: one issuer
+        // warp per tile, converged, one ELECTed lane, descriptors built once and advanced by adds.
+        const int t = warp == 1 ? 0 : 1;
+        constexpr uint32_t idesc_s = idesc_bf16(128, G_KB, false);
+        constexpr uint32_t idesc_o = idesc_bf16(128, D, true);
+        const uint32_t s_tmem = tmem_base + t * TILE_COLS, p_tmem = s_tmem + G_P_COL, o_tmem = s_tmem + G_O_COL;
+        const uint64_t qdesc0 = umma_desc_k_sw128(smem_base + t * G_Q_BYTES);             // + qb * (2 Q tiles)
+        const uint64_t kdesc0 = umma_desc_k_sw128(smem_base + KV_OFF);                     // + stage * (K + V block)
+        const uint64_t vdesc0 = umma_desc_mn_sw128(smem_base + KV_OFF + G_KV_BYTES);
+        auto issue_s = [&](int qb, int st) {
+            if (elect_one()) {
+                const uint64_t ad = qdesc0 + (uint64_t)(qb * (2 * G_Q_BYTES >> 4)), bd = kdesc0 + (uint64_t)(st * (G_STAGE_BYTES >> 4));
+                if (!G_ABLATE(4)) {
+#pragma unroll
+                    for (int k = 0; k < D / 16; ++k) umma_bf16(s_tmem, ad + 2 * k, bd + 2 * k, idesc_s, k ? 1u : 0u);   // +32 B along K
+                }
+                umma_commit(&s_full[t]);
+            }
+            __syncwarp();
+        };
+        int stage = 0;
+        uint32_t phase = 0, pph = 0, fph = 0;          // K/V ring, p_full[t], s_free[t]
+        int it = 0;
+        int u = blockIdx.x;
+        if (u < a.nunits && (t == 0 || !(odd_tiles && (u % a.npairs) == last_tile_pair))) {   // prologue: S(0) of the first unit
+            mbar_wait(&q_full[0], 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+        }
+        for (; u < a.nunits; u += gridDim.x, ++it) {
+            const bool two = !(odd_tiles && (u % a.npairs) == last_tile_pair);
+            const bool valid = t == 0 || two;
+            const int un = u + (int)gridDim.x;
+            const bool valid_next = un < a.nunits && (t == 0 || !(odd_tiles && (un % a.npairs) == last_tile_pair));
+            const int ncommit = (t == 0 && !two) ? 2 : 1;     // K/V and Q buffers are released by two arrivals
+            for (int j = 0; j < a.nblocks; ++j) {
+                const int nstage = (stage + 1 == G_STAGES) ? 0 : stage + 1;
+                const uint32_t nphase = (stage + 1 == G_STAGES) ? phase ^ 1 : phase;
+                const bool last = j + 1 == a.nblocks;
+                // (1) S of the successor block as soon as the softmax warpgroup holds S(j) in registers: the score MMA of
+                //     block j+1 runs under the exponentials of block j
+                if (valid) {
+                    mbar_wait(&s_free[t], fph);
+                    fph ^= 1;
+                    if (lane == 0 && t == 0) G_TRACE(1, 1 + t);
+                }
+                if (last ? valid_next : valid) {
+                    if (last) mbar_wait(&q_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+                    mbar_wait(&kv_full[nstage], nphase);
+                    tc_fence_after();
+                    issue_s(last ? (it + 1) & 1 : it & 1, nstage);
+                    if (lane == 0 && t == 0) G_TRACE(1, 7 + t);
+                }
+                // (2) O += P(j) V(j) once the probabilities are in TMEM; the commits behind it also release the K / V stage
+                //     and, on the last block, the Q buffer (every MMA of this tile that reads them is older)
+                if (valid) {
+                    mbar_wait(&p_full[t], pph);
+                    pph ^= 1;
+                    tc_fence_after();
+                    if (lane == 0 && t == 0) G_TRACE(1, 5 + t);
+                    if (elect_one()) {
+                        if (!G_ABLATE(2)) {
+                            const uint64_t bd = vdesc0 + (uint64_t)(stage * (G_STAGE_BYTES >> 4));
+#pragma unroll
+                            for (int k = 0; k < G_KB / 16; ++k)   // 16 keys = 2048 B of the MN-major V block, 8 TMEM columns of P
+                                umma_bf16_ts(o_tmem, p_tmem + k * 8, bd + 128 * k, idesc_o, (j == 0 && k == 0) ? 0u : 1u);
+                        }
+                        umma_commit(&pv_done[t]);
+                        umma_commit(&kv_empty[stage]);
+                        if (ncommit == 2) umma_commit(&kv_empty[stage]);
+                        if (last) {
+                            umma_commit(&q_empty[it & 1]);
+                            if (ncommit == 2) umma_commit(&q_empty[it & 1]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0 && t == 0) G_TRACE(1, 9 + t);
+                }
+                stage = nstage;
+                phase = nphase;
+            }
+        }
+    } else {  // ---------------- softmax + epilogue warpgroups ----------------
+        const int t = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t tile_tmem = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * TILE_COLS;
+        uint32_t sph = 0, vph = 0;
+        for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+            const int pr = u % a.npairs, bh = u / a.npairs, h = bh % a.heads, b = bh / a.heads;
+            if (t == 1 && odd_tiles && pr == last_tile_pair) continue;
+            const int q0 = (2 * pr + t) * G_QT;               // first query of this tile inside the problem
+            const bool warp_has_rows = q0 + quarter * 32 < a.S;
+            float m = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            for (int j = 0; j < a.nblocks; ++j) {
+                mbar_wait(&s_full[t], sph);
+                sph ^= 1;
+                tc_fence_after();
+                if (quarter == 2 && lane == 0) G_TRACE(2 + t, 1);
+                uint32_t r0[32], r1[32], r2[32], r3[16];
+                if (warp_has_rows) {
+                    tmem_ld_32x32(tile_tmem, r0);
+                    tmem_ld_32x32(tile_tmem + 32, r1);
+                    tmem_ld_32x32(tile_tmem + 64, r2);
+                    tmem_ld_32x16(tile_tmem + 96, r3);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[t]);      // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
+                if (quarter == 2 && lane == 0) G_TRACE(2 + t, 2);
+                bool rescale = false;
+                float alpha = 1.0f;
+                uint32_t pk[16];
+                const float sc = a.scale_log2;
+                auto expo = [&](uint32_t sbits) {
+                    const float x = fmaf(__uint_as_float(sbits), sc, -m);
+                    return G_ABLATE(1) ? x : ex2_approx(x);
+                };
+                if (warp_has_rows) {
+                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3])));
+                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])));
+                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3])));
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r2[i + 2]), __uint_as_float(r2[i + 3])));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(r3[i]), __uint_as_float(r3[i + 1])));
+                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(r3[i + 2]), __uint_as_float(r3[i + 3])));
+                    }
+                    const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;
+                    if (j == 0) {
+                        m = mb;
+                    } else {
+                        const bool need = mb - m > 8.0f;
+                        rescale = __any_sync(0xffffffffu, need) != 0;   // rare: raise the maximum, rescale l here and O below
+                        if (rescale) {
+                            alpha = need ? ex2_approx(m - mb) : 1.0f;
+                            if (need) m = mb;
+                            l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float p0 = expo(r0[2 * i]), p1 = expo(r0[2 * i + 1]), p2 = expo(r0[2 * i + 2]), p3 = expo(r0[2 * i + 3]);
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        pk[i] = pack_bf16(p0, p1); pk[i + 1] = pack_bf16(p2, p3);
+                    }
+                }
+                if (quarter == 2 && lane == 0) G_TRACE(2 + t, 3);
+                if (j > 0) {     // PV(j-1) complete (issued more than a quarter block of exponentials ago): P may be overwritten, O rescaled
+                    mbar_wait(&pv_done[t], vph);
+                    vph ^= 1;
+                    tc_fence_after();
+                }
+                if (warp_has_rows) {
+                    if (rescale) {
+#pragma unroll 1
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t o[32];
+                            tmem_ld_32x32(tile_tmem + G_O_COL + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_32x32(tile_tmem + G_O_COL + c * 32, o);
+                        }
+                    }
+                    tmem_st_32x16(tile_tmem + G_P_COL, pk);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float p0 = expo(r1[2 * i]), p1 = expo(r1[2 * i + 1]), p2 = expo(r1[2 * i + 2]), p3 = expo(r1[2 * i + 3]);
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        pk[i] = pack_bf16(p0, p1); pk[i + 1] = pack_bf16(p2, p3);
+                    }
+                    tmem_st_32x16(tile_tmem + G_P_COL + 16, pk);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float p0 = expo(r2[2 * i]), p1 = expo(r2[2 * i + 1]), p2 = expo(r2[2 * i + 2]), p3 = expo(r2[2 * i + 3]);
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        pk[i] = pack_bf16(p0, p1); pk[i + 1] = pack_bf16(p2, p3);
+                    }
+                    tmem_st_32x16(tile_tmem + G_P_COL + 32, pk);
+                    uint32_t pk8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const float p0 = expo(r3[2 * i]), p1 = expo(r3[2 * i + 1]), p2 = expo(r3[2 * i + 2]), p3 = expo(r3[2 * i + 3]);
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        pk8[i] = pack_bf16(p0, p1); pk8[i + 1] = pack_bf16(p2, p3);
+                    }
+                    tmem_st_32x8(tile_tmem + G_P_COL + 48, pk8);
+                }
+                if (quarter == 2 && lane == 0) G_TRACE(2 + t, 4);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);
+                if (quarter == 2 && lane == 0) G_TRACE(2 + t, 5);
+            }
+            // epilogue: O / l -> bf16 -> token-major output row of this query
+            mbar_wait(&pv_done[t], vph);
+            vph ^= 1;
+            tc_fence_after();
+            const int q = q0 + row;
+            const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+            __nv_bfloat16* dst = a.o + ((size_t)b * a.S + q) * a.ldo + h * D;
+            if (warp_has_rows) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tile_tmem + G_O_COL + c * 32, r);
+                    tmem_ld_wait();
+                    if (q < a.S) {
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            uint4 v;
+                            v.x = pack_bf16(__uint_as_float(r[8 * qq]) * inv, __uint_as_float(r[8 * qq + 1]) * inv);
+                            v.y = pack_bf16(__uint_as_float(r[8 * qq + 2]) * inv, __uint_as_float(r[8 * qq + 3]) * inv);
+                            v.z = pack_bf16(__uint_as_float(r[8 * qq + 4]) * inv, __uint_as_float(r[8 * qq + 5]) * inv);
+                            v.w = pack_bf16(__uint_as_float(r[8 * qq + 6]) * inv, __uint_as_float(r[8 * qq + 7]) * inv);
+                            *reinterpret_cast<uint4*>(dst + c * 32 + qq * 8) = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---- host: 5-D tensor maps over the fused projection buffer --------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -384,6 +773,7 @@ int init() {
     VPU_REQUIRE(prop.major == 10, "window attention needs an sm_100a device");
     g_sms = prop.multiProcessorCount;
     VPU_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(global_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
@@ -411,7 +801,63 @@ int make_map(CUtensorMap* tm, const void* ptr, int ld, int images, int grid, int
     return 0;
 }
 
+// plain 2-D map over a token-major [rows, ld] bf16 buffer: box = 64 columns x box_rows rows, 128B swizzle
+int make_map_2d(CUtensorMap* tm, const void* ptr, int ld, long long rows, int box_rows) {
+    Key key{ptr, ld, (int)rows, box_rows, -1};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) { *tm = it->second; return 0; }
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)D, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPU_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (2-D attention map) failed with %d", (int)r);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_cache.size() > 1024) g_cache.clear();
+    g_cache[key] = *tm;
+    return 0;
+}
+
 }  // namespace
+
+bool global_attention_tc_supported(const AttnArgs& a, int head_dim) {
+    return head_dim == D && a.qmap.mode == 0 && a.kmap.mode == 0 && a.Sq == a.Sk && a.Sk % G_KB == 0 && a.Sk >= 2 * G_KB &&
+           a.qmap.per_prob == a.Sq && a.kmap.per_prob == a.Sk && a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 &&
+           a.ldo % 8 == 0 && a.qoff % 8 == 0 && a.koff % 8 == 0 && a.voff % 8 == 0 &&
+           ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
+             reinterpret_cast<uintptr_t>(a.o)) & 15) == 0;
+}
+
+static unsigned long long* g_trace = nullptr;
+static int g_trace_cap = 0;
+void attention_debug_trace(unsigned long long* dev_buf, int cap) { g_trace = dev_buf; g_trace_cap = cap; }
+
+int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
+    if (int rc = init()) return rc;
+    const long long rows = (long long)a.nprob * a.Sq;
+    CUtensorMap tmQ, tmK, tmV;
+    if (int rc = make_map_2d(&tmQ, a.q, a.ldq, rows, G_QT)) return rc;
+    if (int rc = make_map_2d(&tmK, a.k, a.ldk, rows, G_KB)) return rc;
+    if (int rc = make_map_2d(&tmV, a.v, a.ldv, rows, G_KB)) return rc;
+    GlobArgs g;
+    g.o = a.o; g.ldo = a.ldo; g.heads = a.heads; g.S = a.Sq; g.nblocks = a.Sk / G_KB;
+    g.ntiles = (a.Sq + G_QT - 1) / G_QT; g.npairs = (g.ntiles + 1) / 2;
+    g.nunits = a.nprob * a.heads * g.npairs;
+    g.qcol = a.qoff; g.kcol = a.koff; g.vcol = a.voff; g.scale_log2 = a.scale_log2;
+    static const int ablate = [] { const char* e = getenv("VPU_ATTN_ABLATE"); return e ? atoi(e) : 0; }();
+    g.ablate = ablate;
+    g.trace = g_trace; g.trace_cap = g_trace_cap;
+    const int ctas = g.nunits < g_sms ? g.nunits : g_sms;
+    global_attention_tc_kernel<<<ctas, G_THREADS, G_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, g);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
 
 bool window_attention_tc_supported(const AttnArgs& a, int head_dim) {
     return head_dim == D && a.qmap.mode == 1 && a.qmap.win == WIN && a.qmap.grid % WIN == 0 && a.Sq == SK && a.Sk == SK &&

@@ -184,26 +184,37 @@ constexpr int EPI_PITCH = 36;                        // fp32 words per staged ro
 constexpr int EPI_WARP_WORDS = 32 * EPI_PITCH;       // 4608 B per epilogue warp
 constexpr int EPI_SMEM_BYTES = 8 * EPI_WARP_WORDS * 4;
 
-// erf-GELU (reference nn.GELU(), models_vit.py:14-27) with erf from Abramowitz-Stegun 7.1.28,
-// erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |error| <= 3e-7: 16 instructions and one MUFU instead of
-// the ~30-instruction branchy erff; the bf16 output keeps 8 mantissa bits.
+// erf-GELU (reference nn.GELU(), models_vit.py:14-27) evaluated as x * Phi(x) with
+// Phi(x) = 0.5 (1 + tanh(u)) = 1 / (1 + exp(-2u)), u = x (a + b x^2 + c x^4), (a, b, c) a minimax fit of the erf form:
+// |gelu(x) - x Phi(x)| <= 2.6e-5 for every x (the fit is exact to O(x^3) at 0).  ex2.approx + rcp.approx keep the
+// evaluation error at ~1e-6 (tanh.approx's 2^-11 relative error moved the stress-weights parity test), so the total
+// stays below the half-ulp of the bf16 this epilogue stores.  7 FMA-pipe instructions + two MUFUs per element: the
+// previous Abramowitz-Stegun erf (19 instructions + MUFU) made the fc1 epilogue (32768 elements per CTA tile) longer
+// than the tile's MMA time (A/B on B200, fc1 M=50176: 243 us -> 218 us).
+#ifdef VPU_GELU_AS   // A/B build only: the previous Abramowitz-Stegun 7.1.28 erf (|error| <= 3e-7, 19 instructions + MUFU)
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
     float p = 0.0000430638f;
-    p = fmaf(p, z, 0.0002765672f);
-    p = fmaf(p, z, 0.0001520143f);
-    p = fmaf(p, z, 0.0092705272f);
-    p = fmaf(p, z, 0.0422820123f);
-    p = fmaf(p, z, 0.0705230784f);
-    p = fmaf(p, z, 1.0f);
+    p = fmaf(p, z, 0.0002765672f); p = fmaf(p, z, 0.0001520143f); p = fmaf(p, z, 0.0092705272f);
+    p = fmaf(p, z, 0.0422820123f); p = fmaf(p, z, 0.0705230784f); p = fmaf(p, z, 1.0f);
     p = p * p; p = p * p; p = p * p; p = p * p;
-    float rp;   // rcp.approx: one MUFU, 1 ulp, no range-check slow path (p >= 1; inf -> 0), so the four
-                // GELUs of a lane stay branch-free and interleave (__frcp_rn serialised them behind BSSY/CALL)
+    float rp;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rp) : "f"(p));
-    const float erf_abs = 1.0f - rp;
     const float h = 0.5f * x;
-    return fmaf(h, copysignf(erf_abs, x), h);
+    return fmaf(h, copysignf(1.0f - rp, x), h);
 }
+#else
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float x2 = fminf(x * x, 64.0f);   // the quartic turns over at |x| = 11; Phi is saturated (|u| >= 13.8) from |x| = 8
+    // -2 log2(e) * (a, b, c): v = -2 u log2(e)
+    float t = fmaf(1.014263054e-3f, x2, -1.067757239e-1f);
+    t = fmaf(t, x2, -2.301121339f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));     // e = +inf (x << 0) -> r = 0
+    return x * r;
+}
+#endif
 
 template <int BN, int EK>
 __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, uint32_t tmem_acc, int row_base, int col_base,

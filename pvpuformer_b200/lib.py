@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvpuformer_b200.so")
+LIB_PATH = os.environ.get("VPU_LIB_PATH") or os.path.join(HERE, "libvpuformer_b200.so")   # env: A/B builds during development
 
 VPU_F32, VPU_BF16, VPU_I32, VPU_F64, VPU_U8 = 0, 1, 2, 3, 4
 
@@ -54,6 +54,7 @@ SIGNATURES = {
     "vpu_gemm_pixel_shuffle": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "vpu_attention": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
+    "vpu_debug_attention_trace": (c_int, [c_void_p, c_int]),
     "vpu_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
     "vpu_groupnorm_nhwc": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -144,6 +144,26 @@ def test_window_attention_tcgen05_many_problems():
     assert (o.float() - refw).abs().max().item() < 1e-2 * max(1.0, refw.abs().max().item())
 
 
+@pytest.mark.parametrize("heads,B,amp", [(12, 20, 1.0), (16, 5, 6.0)])
+def test_global_attention_tcgen05_many_problems(heads, B, amp):
+    """ViT-B / ViT-L global attention (S=784, d=64) on the tcgen05 flash kernel with more work units than SMs (every
+    CTA loops over units: Q double buffer, K/V ring wrap, single-tile last pairs between two-tile units).  amp=6
+    gives score blocks whose maxima differ by far more than 2^8, so the lazy O / l rescale path runs."""
+    from pvpuformer_b200 import ops
+    hd, N = 64, 784
+    C = heads * hd
+    qkv = _rand_bf16((B * N, 3 * C), 33, amp)
+    if amp > 1.0:     # the late keys carry the large scores: the running maximum has to be raised mid-stream
+        qkv.view(B, N, 3 * C)[:, : N // 2, C:2 * C] *= 0.05
+    scale = hd ** -0.5
+    t = qkv.view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    ref = _attn_ref(t[0], t[1], t[2], scale).transpose(1, 2).reshape(B * N, C)
+    o = ops.attention(qkv, qkv, qkv, N, N, heads, hd, B, scale, 0, C, 2 * C)
+    torch.cuda.synchronize()
+    assert not torch.isnan(o.float()).any()
+    assert (o.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("C", [768, 1024, 1280])
 def test_attention_dma_shapes(C):
     from pvpuformer_b200 import ops
