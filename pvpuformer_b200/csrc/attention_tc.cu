@@ -85,11 +85,6 @@ __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU; arguments 
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // MN-major 128B-swizzled operand (V: rows = keys (K), 64 head-dim elements = one 128-byte row):

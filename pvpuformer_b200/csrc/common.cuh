@@ -94,6 +94,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of the (converged) warp.  Issue code for TMA / tcgen05 belongs under `if (elect_one())` in a warp that runs its
+// loop converged, NOT under `if (lane == 0)`: there nvcc cannot prove single-lane execution and wraps every uniform-datapath
+// instruction in an ELECT / R2UR / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA ----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");

@@ -180,6 +180,13 @@ enum EpiKind {
     EK_PS = 7          // out bf16 = acc + bias, pixel-shuffle store  (ConvTranspose2d k=2 s=2 of the neck)
 };
 
+// measurement-only ablation (VPU_GEMM_ABLATE) is compiled in with -DVPU_GEMM_DEBUG: the check sat in the MMA issue loop
+#ifdef VPU_GEMM_DEBUG
+#define GEMM_ABLATE(bit) (d.ablate & (bit))
+#else
+#define GEMM_ABLATE(bit) 0
+#endif
+
 constexpr int EPI_PITCH = 36;                        // fp32 words per staged row
 constexpr int EPI_WARP_WORDS = 32 * EPI_PITCH;       // 4608 B per epilogue warp
 constexpr int EPI_SMEM_BYTES = 8 * EPI_WARP_WORDS * 4;
@@ -381,51 +388,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kblks = (d.K + BK - 1) / BK;
 
     if (warp == 0) {
-        if (lane == 0) {  // ---------------- TMA producer ----------------
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_blks, n_blk = tile % n_blks;
-                int brow = n_blk * BN;
-                if (e.m_per_batch > 0) brow += ((m_blk * BM) / e.m_per_batch) * e.b_rows_per_batch;
-                for (int kb = 0; kb < kblks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ---------------- TMA producer (converged warp, one elected lane issues; see gemm_tc2_kernel) ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+            int brow = n_blk * BN;
+            if (e.m_per_batch > 0) brow += ((m_blk * BM) / e.m_per_batch) * e.b_rows_per_batch;
+            for (int kb = 0; kb < kblks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
                     tma_load_2d(sa + C::A_BYTES, &tmB, &full_bar[stage], kb * BK, brow);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ---------------- MMA issuer (converged warp, one elected lane issues) ----------------
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        const uint64_t adesc0 = umma_desc_k_sw128(smem_base), bdesc0 = umma_desc_k_sw128(smem_base + C::A_BYTES);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
+            for (int kb = 0; kb < kblks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
-                for (int kb = 0; kb < kblks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + C::A_BYTES;
+                if (elect_one()) {
+                    const uint64_t soff = (uint64_t)(stage * (C::STAGE_BYTES >> 4));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
-                                  idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(d_tmem, adesc0 + soff + 2 * k, bdesc0 + soff + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (kb + 1 == kblks) umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
                 }
-                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     } else {  // ---------------- epilogue warps ----------------
         const int quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are this warp's
@@ -524,19 +533,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int nst = d.stages > 0 && d.stages < C::STAGES ? d.stages : C::STAGES;
 
     if (warp == 0) {
-        if (lane == 0) {  // ---------------- TMA producer (both CTAs) ----------------
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = pair; tile < tiles; tile += npairs) {
-                const int m_blk = tile / n_blks, n_blk = tile % n_blks;
-                const int arow = (m_blk * PP + pr) * 2 * BM + rank * BM;
-                // this CTA fetches 1/PP of the B half its pair position needs and multicasts it to the CTAs at the same
-                // position in every pair of the cluster
-                const int brow = n_blk * BN + rank * (BN / 2) + pr * (BN / 2 / PP);
-                const uint16_t bmask = (uint16_t)(PP == 1 ? 0 : ((1u << rank) | (1u << (2 + rank))));
-                for (int kb = 0; kb < kblks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (d.ablate & 1) {
+        // ---------------- TMA producer (both CTAs) ----------------
+        // The producer and the MMA issuer run as whole converged warps with one ELECTed lane doing the issue: inside an
+        // `if (lane == 0)` region nvcc wraps every tcgen05.mma / commit in an elect + BRA.U.ANY loop and rebuilds both
+        // 64-bit descriptors per instruction (~120 SASS instructions per k-block; a lone warp retires a dependent
+        // instruction every ~5-8 clk, so issuing one k-block took longer than its 512 clk of MMA work and capped the tensor
+        // pipe at 67 %, ncu round 1c).  Descriptors are built once and advanced by adding to their address field.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair; tile < tiles; tile += npairs) {
+            const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+            const int arow = (m_blk * PP + pr) * 2 * BM + rank * BM;
+            // this CTA fetches 1/PP of the B half its pair position needs and multicasts it to the CTAs at the same
+            // position in every pair of the cluster
+            const int brow = n_blk * BN + rank * (BN / 2) + pr * (BN / 2 / PP);
+            const uint16_t bmask = (uint16_t)(PP == 1 ? 0 : ((1u << rank) | (1u << (2 + rank))));
+            for (int kb = 0; kb < kblks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    if (GEMM_ABLATE(1)) {
                         if (leader) mbar_arrive(&full_bar[stage]);
                     } else {
                         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
@@ -547,13 +562,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         else
                             tma_load_2d_2sm_mc(sa + C::A_BYTES + pr * (C::B_BYTES / PP), &tmB, &full_bar[stage], kb * BK, brow, bmask);
                     }
-                    if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (leader && lane == 0) {  // ---------------- MMA issuer (leader CTA only) ----------------
+        if (leader) {  // ---------------- MMA issuer (leader CTA only; converged warp, one elected lane) ----------------
             constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            const uint64_t adesc0 = umma_desc_k_sw128(smem_base), bdesc0 = umma_desc_k_sw128(smem_base + C::A_BYTES);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -565,18 +582,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int kb = 0; kb < kblks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + C::A_BYTES;
-                    if (!(d.ablate & 2))
+                    if (elect_one()) {
+                        const uint64_t soff = (uint64_t)(stage * (C::STAGE_BYTES >> 4));      // descriptor address field: bytes >> 4
+                        if (!GEMM_ABLATE(2)) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
-                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BK / 16; ++k)                                 // +32 B along K per UMMA
+                                umma_bf16_2sm(d_tmem, adesc0 + soff + 2 * k, bdesc0 + soff + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_2sm(&empty_bar[stage], kAllMask);   // this pair is done with the stage: tell every CTA that writes into it
+                        if (kb + 1 == kblks) umma_commit_2sm(&tfull_bar[acc], pair_mask);   // accumulator halves complete in both CTAs of this pair
                     }
-                    umma_commit_2sm(&empty_bar[stage], kAllMask);   // this pair is done with the stage: tell every CTA that writes into it
+                    __syncwarp();
                     if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2sm(&tfull_bar[acc], pair_mask); // accumulator halves complete in both CTAs of this pair
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
