@@ -154,8 +154,7 @@ Plan make_plan(const vpu_context& h, int B) {
     p.add("P16", M * h.d.out_dims[2] * 2);
     p.add("D32a", (size_t)B * gh * gh * h.d32() * 2);
     p.add("P32", (size_t)B * gh * gh * h.d.out_dims[3] * 2);
-    p.add("gn_partial", (size_t)B * GN_MAX_CHUNKS * 8);
-    p.add("gn_stats", (size_t)B * 8);
+    p.add("gn_sums", (size_t)8 * B * 2 * sizeof(double));    // 8 GroupNorms x [B][sum, sum of squares]
     // head
     const size_t res[4] = {g4, g2, g, gh};
     for (int i = 0; i < 4; ++i) {
@@ -202,25 +201,38 @@ struct Fwd {
     const __nv_bfloat16* Wb(const std::string& key) { return W<__nv_bfloat16>(key); }
     const float* Wf(const std::string& key) { return W<float>(key); }
 
+    // GroupNorm fusion arguments of a neck GEMM (Epi::gn_*): statistics out, and / or the producer's GroupNorm folded in
+    struct Gn {
+        double* out = nullptr;
+        const double* in = nullptr;
+        const float* wg = nullptr;
+        int rows = 0;
+        double in_count = 0;
+    };
+    void set_gn(Epi& e, const Gn& g) {
+        e.gn_out = g.out; e.gn_in = g.in; e.gn_wg = g.wg; e.gn_rows = g.rows; e.gn_in_count = (float)g.in_count;
+    }
     // out = act(A W^T + bias [+ tab] [+ res])
     int gemm(const __nv_bfloat16* A, int lda, const std::string& wkey, int M, int Nn, int K, const float* bias, void* out,
              bool out_bf16, int ldo, int act = ACT_NONE, const void* res = nullptr, bool res_bf16 = false, int ldr = 0,
-             const float* tab = nullptr, int tab_rows = 0) {
+             const float* tab = nullptr, int tab_rows = 0, const Gn* gn = nullptr) {
         GemmProblem p;
         p.A = A; p.W = Wb(wkey); p.M = M; p.N = Nn; p.K = K; p.lda = lda;
         p.ldw = (int)h.w.at(wkey).shape[1];
         p.w_rows = Nn;
         p.epi.out = out; p.epi.out_bf16 = out_bf16; p.epi.ldo = ldo; p.epi.bias = bias; p.epi.act = act;
         p.epi.res = res; p.epi.res_bf16 = res_bf16; p.epi.ldr = ldr; p.epi.bias2d = tab; p.epi.bias2d_rows = tab_rows;
+        if (gn) set_gn(p.epi, *gn);
         const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0));
         return timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
     }
     int gemm_ps(const __nv_bfloat16* A, const std::string& wkey, const float* bias4, int M, int cout, int K, int g,
-                __nv_bfloat16* out) {
+                __nv_bfloat16* out, const Gn* gn = nullptr) {
         GemmProblem p;
         p.A = A; p.W = Wb(wkey); p.M = M; p.N = 4 * cout; p.K = K; p.lda = K; p.ldw = K; p.w_rows = 4 * cout;
         p.epi.out = out; p.epi.out_bf16 = 1; p.epi.ldo = cout; p.epi.bias = bias4; p.epi.mode = EPI_PIXEL_SHUFFLE;
         p.epi.ps_g = g; p.epi.ps_cout = cout;
+        if (gn) set_gn(p.epi, *gn);
         const double by = 2.0 * ((double)M * K + 4.0 * cout * K + 4.0 * M * cout);
         return timed("gemm", 8.0 * M * cout * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
     }
@@ -232,10 +244,10 @@ struct Fwd {
         const double by = (double)rows * h.C() * (4 + (of ? 4 : 0) + (ob ? 2 : 0) + (ope ? 6 : 0));
         return timed("ln", 0, by, [&] { return layernorm_launch(a, h.C(), s); });
     }
-    int gn(__nv_bfloat16* x, size_t per_sample, int Cc, const std::string& key, int gelu) {
-        return timed("gn", 0, 6.0 * B * (double)per_sample, [&] {
-            return groupnorm_launch(x, B, per_sample, Cc, Wf(key + ".g"), Wf(key + ".b"), gelu, buf<float2>("gn_partial"),
-                                    buf<float2>("gn_stats"), s);
+    // GroupNorm apply (+GELU) with the statistics the producing GEMM accumulated: one read + one write of x
+    int gn(__nv_bfloat16* x, size_t per_sample, int Cc, const std::string& key, int gelu, const double* sums) {
+        return timed("gn", 0, 4.0 * B * (double)per_sample, [&] {
+            return groupnorm_apply_launch(x, B, per_sample, Cc, Wf(key + ".g"), Wf(key + ".b"), gelu, sums, s);
         });
     }
     int attn(const __nv_bfloat16* q, int ldq, int qoff, const __nv_bfloat16* k, int ldk, int koff, const __nv_bfloat16* v,
@@ -422,25 +434,43 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     const int d4 = h.d4(), d8 = h.d8(), d32 = h.d32();
     const int* od = h.d.out_dims;
     const size_t g2 = 2 * g, g4 = 4 * g, gh = g / 2;
-    RUN(f.gemm_ps(X0b, "d4.a.w", f.Wf("d4.a.b"), M, d4, C, g, f.buf<bf>("D4a")));
-    RUN(f.gn(f.buf<bf>("D4a"), g2 * g2 * d4, d4, "d4.gn1", 1));
-    RUN(f.gemm_ps(f.buf<bf>("D4a"), "d4.b.w", f.Wf("d4.b.b"), (int)(B * g2 * g2), d4 / 2, d4, (int)g2, f.buf<bf>("D4b")));
-    RUN(f.gn(f.buf<bf>("D4b"), g4 * g4 * (d4 / 2), d4 / 2, "d4.gn2", 0));
-    RUN(f.gemm(f.buf<bf>("D4b"), d4 / 2, "d4.c.w", (int)(B * g4 * g4), od[0], d4 / 2, f.Wf("d4.c.b"), f.buf<bf>("P4"), true, od[0]));
-    RUN(f.gn(f.buf<bf>("P4"), g4 * g4 * od[0], od[0], "d4.gn3", 1));
+    // GroupNorm(1, C) is fused into the GEMMs on both sides (Epi::gn_*): every GEMM accumulates the per-sample sum / sum of
+    // squares of its fp32 outputs in its epilogue, the three GroupNorms that are not followed by GELU (d4.gn2, d8.gn1,
+    // d32.gn1) are folded into the consuming 1x1 conv, and the other five need one apply (+GELU) pass and no statistics pass.
+    double* sums = f.buf<double>("gn_sums");
+    VPU_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)8 * B * 2 * sizeof(double), s));
+    auto S = [&](int i) { return sums + (size_t)i * B * 2; };
+    typedef Fwd::Gn Gn;
+    Gn gn;
+    gn = Gn(); gn.out = S(0); gn.rows = N;
+    RUN(f.gemm_ps(X0b, "d4.a.w", f.Wf("d4.a.b"), M, d4, C, g, f.buf<bf>("D4a"), &gn));
+    RUN(f.gn(f.buf<bf>("D4a"), g2 * g2 * d4, d4, "d4.gn1", 1, S(0)));
+    gn = Gn(); gn.out = S(1); gn.rows = (int)(g2 * g2);
+    RUN(f.gemm_ps(f.buf<bf>("D4a"), "d4.b.w", f.Wf("d4.b.b"), (int)(B * g2 * g2), d4 / 2, d4, (int)g2, f.buf<bf>("D4b"), &gn));
+    gn = Gn(); gn.in = S(1); gn.in_count = (double)(g4 * g4) * (d4 / 2); gn.wg = f.Wf("d4.c.wg"); gn.out = S(2); gn.rows = (int)(g4 * g4);
+    RUN(f.gemm(f.buf<bf>("D4b"), d4 / 2, "d4.c.w", (int)(B * g4 * g4), od[0], d4 / 2, f.Wf("d4.c.b"), f.buf<bf>("P4"), true, od[0],
+               ACT_NONE, nullptr, false, 0, nullptr, 0, &gn));
+    RUN(f.gn(f.buf<bf>("P4"), g4 * g4 * od[0], od[0], "d4.gn3", 1, S(2)));
 
-    RUN(f.gemm_ps(f.buf<bf>("x2"), "d8.a.w", f.Wf("d8.a.b"), M, d8, C, g, f.buf<bf>("D8a")));
-    RUN(f.gn(f.buf<bf>("D8a"), g2 * g2 * d8, d8, "d8.gn1", 0));
-    RUN(f.gemm(f.buf<bf>("D8a"), d8, "d8.b.w", (int)(B * g2 * g2), od[1], d8, f.Wf("d8.b.b"), f.buf<bf>("P8"), true, od[1]));
-    RUN(f.gn(f.buf<bf>("P8"), g2 * g2 * od[1], od[1], "d8.gn2", 1));
+    gn = Gn(); gn.out = S(3); gn.rows = N;
+    RUN(f.gemm_ps(f.buf<bf>("x2"), "d8.a.w", f.Wf("d8.a.b"), M, d8, C, g, f.buf<bf>("D8a"), &gn));
+    gn = Gn(); gn.in = S(3); gn.in_count = (double)(g2 * g2) * d8; gn.wg = f.Wf("d8.b.wg"); gn.out = S(4); gn.rows = (int)(g2 * g2);
+    RUN(f.gemm(f.buf<bf>("D8a"), d8, "d8.b.w", (int)(B * g2 * g2), od[1], d8, f.Wf("d8.b.b"), f.buf<bf>("P8"), true, od[1],
+               ACT_NONE, nullptr, false, 0, nullptr, 0, &gn));
+    RUN(f.gn(f.buf<bf>("P8"), g2 * g2 * od[1], od[1], "d8.gn2", 1, S(4)));
 
-    RUN(f.gemm(f.buf<bf>("x3"), C, "d16.a.w", M, od[2], C, f.Wf("d16.a.b"), f.buf<bf>("P16"), true, od[2]));
-    RUN(f.gn(f.buf<bf>("P16"), (size_t)N * od[2], od[2], "d16.gn1", 1));
+    gn = Gn(); gn.out = S(5); gn.rows = N;
+    RUN(f.gemm(f.buf<bf>("x3"), C, "d16.a.w", M, od[2], C, f.Wf("d16.a.b"), f.buf<bf>("P16"), true, od[2], ACT_NONE, nullptr, false, 0,
+               nullptr, 0, &gn));
+    RUN(f.gn(f.buf<bf>("P16"), (size_t)N * od[2], od[2], "d16.gn1", 1, S(5)));
 
-    RUN(f.gemm(f.buf<bf>("x4"), 4 * C, "d32.a.w", (int)(B * gh * gh), d32, 4 * C, f.Wf("d32.a.b"), f.buf<bf>("D32a"), true, d32));
-    RUN(f.gn(f.buf<bf>("D32a"), gh * gh * d32, d32, "d32.gn1", 0));
-    RUN(f.gemm(f.buf<bf>("D32a"), d32, "d32.b.w", (int)(B * gh * gh), od[3], d32, f.Wf("d32.b.b"), f.buf<bf>("P32"), true, od[3]));
-    RUN(f.gn(f.buf<bf>("P32"), gh * gh * od[3], od[3], "d32.gn2", 1));
+    gn = Gn(); gn.out = S(6); gn.rows = (int)(gh * gh);
+    RUN(f.gemm(f.buf<bf>("x4"), 4 * C, "d32.a.w", (int)(B * gh * gh), d32, 4 * C, f.Wf("d32.a.b"), f.buf<bf>("D32a"), true, d32,
+               ACT_NONE, nullptr, false, 0, nullptr, 0, &gn));
+    gn = Gn(); gn.in = S(6); gn.in_count = (double)(gh * gh) * d32; gn.wg = f.Wf("d32.b.wg"); gn.out = S(7); gn.rows = (int)(gh * gh);
+    RUN(f.gemm(f.buf<bf>("D32a"), d32, "d32.b.w", (int)(B * gh * gh), od[3], d32, f.Wf("d32.b.b"), f.buf<bf>("P32"), true, od[3],
+               ACT_NONE, nullptr, false, 0, nullptr, 0, &gn));
+    RUN(f.gn(f.buf<bf>("P32"), gh * gh * od[3], od[3], "d32.gn2", 1, S(7)));
 
     // ---- A16: head ----
     f.stage = "head";
@@ -533,11 +563,12 @@ std::vector<Need> needed_weights(const vpu_context& h) {
     lin("dmaf.o", C, Ci); nrm("dmaf.n", C);
     const int64_t d4 = h.d4(), d8 = h.d8(), d32 = h.d32();
     const int* od = h.d.out_dims;
-    lin("d4.a", 4 * d4, C); nrm("d4.gn1", d4); lin("d4.b", 4 * (d4 / 2), d4); nrm("d4.gn2", d4 / 2);
-    lin("d4.c", od[0], d4 / 2); nrm("d4.gn3", od[0]);
-    lin("d8.a", 4 * d8, C); nrm("d8.gn1", d8); lin("d8.b", od[1], d8); nrm("d8.gn2", od[1]);
+    // d4.gn2 / d8.gn1 / d32.gn1 are folded into the weights of the conv that follows them (".wg" = row sums of W diag(gamma))
+    lin("d4.a", 4 * d4, C); nrm("d4.gn1", d4); lin("d4.b", 4 * (d4 / 2), d4);
+    lin("d4.c", od[0], d4 / 2); v.push_back({"d4.c.wg", VPU_F32, {od[0]}}); nrm("d4.gn3", od[0]);
+    lin("d8.a", 4 * d8, C); lin("d8.b", od[1], d8); v.push_back({"d8.b.wg", VPU_F32, {od[1]}}); nrm("d8.gn2", od[1]);
     lin("d16.a", od[2], C); nrm("d16.gn1", od[2]);
-    lin("d32.a", d32, 4 * C); nrm("d32.gn1", d32); lin("d32.b", od[3], d32); nrm("d32.gn2", od[3]);
+    lin("d32.a", d32, 4 * C); lin("d32.b", od[3], d32); v.push_back({"d32.b.wg", VPU_F32, {od[3]}}); nrm("d32.gn2", od[3]);
     const int64_t hc = h.d.head_channels;
     for (int i = 0; i < 4; ++i) {
         lin("hd.c" + std::to_string(i), hc, od[i]);

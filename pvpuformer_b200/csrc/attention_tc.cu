@@ -158,80 +158,87 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
     const int nw2 = a.nwin_side * a.nwin_side;
 
     if (warp == 0) {
-        if (lane == 0) {  // ---------------- TMA producer ----------------
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int p = blockIdx.x; p < a.nprob; p += gridDim.x) {
-                const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
-                const int wi = w / a.nwin_side, wj = w % a.nwin_side;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ---------------- TMA producer (converged warp, one elected lane issues; see common.cuh elect_one) ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int p = blockIdx.x; p < a.nprob; p += gridDim.x) {
+            const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
+            const int wi = w / a.nwin_side, wj = w % a.nwin_side;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full_bar[stage], TX_BYTES);
                 uint8_t* st = smem + stage * STAGE_BYTES;
                 tma_load_5d(st, &tmQ0, &full_bar[stage], a.qcol + h * D, 0, wj, wi * WIN, b);
                 tma_load_5d(st + Q_TILE_BYTES, &tmQ1, &full_bar[stage], a.qcol + h * D, 0, wj, wi * WIN + T0_IROWS, b);
                 tma_load_5d(st + 2 * Q_TILE_BYTES, &tmKV, &full_bar[stage], a.kcol + h * D, 0, wj, wi * WIN, b);
                 tma_load_5d(st + 2 * Q_TILE_BYTES + KV_BYTES, &tmKV, &full_bar[stage], a.vcol + h * D, 0, wj, wi * WIN, b);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc_s = idesc_bf16(128, SKP, false);
-            constexpr uint32_t idesc_o = idesc_bf16(128, D, true);
-            auto issue_s = [&](int t, uint32_t st_addr) {
-                const uint32_t q_addr = st_addr + t * Q_TILE_BYTES, k_addr = st_addr + 2 * Q_TILE_BYTES;
+        // ---------------- MMA issuer (converged warp, one elected lane; descriptors advanced by adds) ----------------
+        // 34 tcgen05.mma per problem: under `if (lane == 0)` each cost ~130 clk of issue (elect / BRA.U.ANY loop + descriptor
+        // rebuild from a lone warp), more than the softmax of the problem.
+        constexpr uint32_t idesc_s = idesc_bf16(128, SKP, false);
+        constexpr uint32_t idesc_o = idesc_bf16(128, D, true);
+        const uint64_t qdesc0 = umma_desc_k_sw128(smem_base), kdesc0 = umma_desc_k_sw128(smem_base + 2 * Q_TILE_BYTES);
+        const uint64_t vdesc0 = umma_desc_mn_sw128(smem_base + 2 * Q_TILE_BYTES + KV_BYTES);
+        auto issue_s = [&](int t, int st) {
+            if (elect_one()) {
+                const uint64_t so = (uint64_t)(st * (STAGE_BYTES >> 4));
+                const uint64_t ad = qdesc0 + so + (uint64_t)(t * (Q_TILE_BYTES >> 4)), bd = kdesc0 + so;
 #pragma unroll
-                for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + t * TILE_COLS, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32),
-                              idesc_s, k ? 1u : 0u);
+                for (int k = 0; k < D / 16; ++k) umma_bf16(tmem_base + t * TILE_COLS, ad + 2 * k, bd + 2 * k, idesc_s, k ? 1u : 0u);
                 umma_commit(&s_full[t]);
-            };
-            auto issue_pv = [&](int t, uint32_t st_addr) {
-                const uint32_t v_addr = st_addr + 2 * Q_TILE_BYTES + KV_BYTES;
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int t, int st, bool release_stage) {
+            if (elect_one()) {
+                const uint64_t bd = vdesc0 + (uint64_t)(st * (STAGE_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < SKP / 16; ++k)
-                    umma_bf16_ts(tmem_base + t * TILE_COLS + O_COL, tmem_base + t * TILE_COLS + k * 8,
-                                 umma_desc_mn_sw128(v_addr + k * 16 * D * 2), idesc_o, k ? 1u : 0u);
+                for (int k = 0; k < SKP / 16; ++k)     // 16 keys = 2048 B of the MN-major V tile, 8 TMEM columns of P
+                    umma_bf16_ts(tmem_base + t * TILE_COLS + O_COL, tmem_base + t * TILE_COLS + k * 8, bd + 128 * k, idesc_o, k ? 1u : 0u);
                 umma_commit(&o_full[t]);
-            };
-            int stage = 0;
-            uint32_t phase = 0;              // full / empty ring
-            uint32_t tphase = 0;             // per-problem phase of s_full / p_full / o_full / s_empty
-            int p = blockIdx.x;
-            if (p < a.nprob) {               // prologue: S0, S1 of the first problem
-                mbar_wait(&full_bar[0], 0);
-                tc_fence_after();
-                issue_s(0, smem_base);
-                issue_s(1, smem_base);
+                if (release_stage) umma_commit(&empty_bar[st]);   // every MMA reading this stage has been issued before
             }
-            for (; p < a.nprob; p += gridDim.x) {
-                const uint32_t st_addr = smem_base + stage * STAGE_BYTES;
-                const bool has_next = p + (int)gridDim.x < a.nprob;
-                const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
-                const uint32_t nphase = (stage + 1 == STAGES) ? phase ^ 1 : phase;
-                const uint32_t nst_addr = smem_base + nstage * STAGE_BYTES;
-                mbar_wait(&p_full[0], tphase);
+            __syncwarp();
+        };
+        int stage = 0;
+        uint32_t phase = 0;              // full / empty ring
+        uint32_t tphase = 0;             // per-problem phase of s_full / p_full / o_full / s_empty
+        int p = blockIdx.x;
+        if (p < a.nprob) {               // prologue: S0, S1 of the first problem
+            mbar_wait(&full_bar[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+        }
+        for (; p < a.nprob; p += gridDim.x) {
+            const bool has_next = p + (int)gridDim.x < a.nprob;
+            const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+            const uint32_t nphase = (stage + 1 == STAGES) ? phase ^ 1 : phase;
+            mbar_wait(&p_full[0], tphase);
+            tc_fence_after();
+            issue_pv(0, stage, false);
+            if (has_next) {
+                mbar_wait(&full_bar[nstage], nphase);
+                mbar_wait(&s_empty[0], tphase);           // tile-0 columns free: epilogue 0 of this problem done
                 tc_fence_after();
-                issue_pv(0, st_addr);
-                if (has_next) {
-                    mbar_wait(&full_bar[nstage], nphase);
-                    mbar_wait(&s_empty[0], tphase);           // tile-0 columns free: epilogue 0 of this problem done
-                    tc_fence_after();
-                    issue_s(0, nst_addr);
-                }
-                mbar_wait(&p_full[1], tphase);
-                tc_fence_after();
-                issue_pv(1, st_addr);
-                umma_commit(&empty_bar[stage]);               // every MMA reading this stage has been issued before
-                if (has_next) {
-                    mbar_wait(&s_empty[1], tphase);
-                    tc_fence_after();
-                    issue_s(1, nst_addr);
-                }
-                stage = nstage;
-                phase = nphase;
-                tphase ^= 1;
+                issue_s(0, nstage);
             }
+            mbar_wait(&p_full[1], tphase);
+            tc_fence_after();
+            issue_pv(1, stage, true);
+            if (has_next) {
+                mbar_wait(&s_empty[1], tphase);
+                tc_fence_after();
+                issue_s(1, nstage);
+            }
+            stage = nstage;
+            phase = nphase;
+            tphase ^= 1;
         }
     } else {  // ---------------- softmax + epilogue warpgroups ----------------
         const int t = (warp - 2) >> 2;                   // row tile of this warpgroup

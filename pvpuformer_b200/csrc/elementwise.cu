@@ -140,12 +140,20 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ partial, int chunk
 }
 // apply: every thread owns one channel octet (gamma / beta live in registers) and strides over pixels
 __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ x, size_t per_sample, int C,
-                                                       const float2* __restrict__ mean_rstd,
+                                                       const float2* __restrict__ mean_rstd, const double* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int gelu) {
     const int b = blockIdx.y, C8 = C / 8, C8z = C8 / gridDim.z;      // wide layers split their channels over grid.z
     const int co = blockIdx.z * C8z + threadIdx.x % C8z, prow = threadIdx.x / C8z, rows_per_block = blockDim.x / C8z;
-    const float2 mr = mean_rstd[b];
+    float2 mr;
+    if (sums) {      // (sum, sum of squares) accumulated by the producing GEMM's epilogue
+        const double inv_n = 1.0 / (double)per_sample, mean = sums[2 * b] * inv_n;
+        double var = sums[2 * b + 1] * inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+    } else {
+        mr = mean_rstd[b];
+    }
     float sc[8], sh[8];
     {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + co * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + co * 8 + 4));
@@ -189,9 +197,26 @@ int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const fl
     const size_t npix = per_sample / C;
     int blocks = (int)((npix + (threads / C8z) - 1) / (threads / C8z));
     if (blocks > 148 * 8) blocks = 148 * 8;
-    gn_apply_kernel<<<dim3(blocks, B, zsplit), threads, 0, stream>>>(x, per_sample, C, mean_rstd, gamma, beta, gelu);
+    gn_apply_kernel<<<dim3(blocks, B, zsplit), threads, 0, stream>>>(x, per_sample, C, mean_rstd, nullptr, gamma, beta, gelu);
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch(3);
+    return 0;
+}
+
+// apply only: the statistics were accumulated by the GEMM epilogue that produced x (Epi::gn_out)
+int groupnorm_apply_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta, int gelu,
+                           const double* sums, cudaStream_t stream) {
+    VPU_REQUIRE(per_sample % 8 == 0 && C % 8 == 0 && per_sample % C == 0, "groupnorm: sizes must be multiples of 8, C must divide the sample");
+    const int C8 = C / 8;
+    int zsplit = 1;
+    while (C8 / zsplit > 256 || C8 % zsplit) ++zsplit;
+    const int C8z = C8 / zsplit, threads = C8z * (256 / C8z);
+    const size_t npix = per_sample / C;
+    int blocks = (int)((npix + (threads / C8z) - 1) / (threads / C8z));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gn_apply_kernel<<<dim3(blocks, B, zsplit), threads, 0, stream>>>(x, per_sample, C, nullptr, sums, gamma, beta, gelu);
+    VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

@@ -23,6 +23,8 @@ constexpr int GN_MAX_CHUNKS = 1024;
 // in-place GroupNorm(1, C) (+GELU) on NHWC bf16 [B, per_sample]; partial: [B, GN_MAX_CHUNKS] float2
 int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta,
                      int gelu, float2* partial, float2* mean_rstd, cudaStream_t stream);
+int groupnorm_apply_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta, int gelu,
+                           const double* sums, cudaStream_t stream);
 
 int qout_gate_launch(const float* q0, const float* q1, const float* q2, const float* q3, int B, int T, int C, float* qout,
                      __nv_bfloat16* qout_bf16, float* cg, cudaStream_t stream);

@@ -37,8 +37,24 @@ unsigned long long launch_count() { return g_launches.load(std::memory_order_rel
 // ------------------------------------------------------------------------------------------
 // Epilogue: CNT consecutive columns [n0, n0+CNT) of output row m.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gn_mean_rstd(const double* sums, int sample, float count, float& rstd, float& mean_rstd) {
+    const double inv_n = 1.0 / (double)count;
+    const double mean = sums[2 * sample] * inv_n;
+    double var = sums[2 * sample + 1] * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double r = 1.0 / sqrt(var + 1e-5);
+    rstd = (float)r;
+    mean_rstd = (float)(mean * r);
+}
+
 template <int CNT>
 __device__ __forceinline__ void epi_store(const Epi& e, int m, int n0, float (&v)[CNT], int N) {
+    if (e.gn_in) {
+        float r, mr;
+        gn_mean_rstd(e.gn_in, m / e.gn_rows, e.gn_in_count, r, mr);
+#pragma unroll
+        for (int t = 0; t < CNT; ++t) v[t] = fmaf(v[t], r, -mr * __ldg(e.gn_wg + n0 + t));
+    }
     if (e.bias) {
         if constexpr (CNT % 4 == 0) {
 #pragma unroll
@@ -106,6 +122,13 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n0, float (&v
                 for (int t = 0; t < CNT; ++t) v[t] += r[t];
             }
         }
+    }
+    if (e.gn_out) {
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int t = 0; t < CNT; ++t) { sum += v[t]; sq = fmaf(v[t], v[t], sq); }
+        atomicAdd(e.gn_out + 2 * (m / e.gn_rows), (double)sum);
+        atomicAdd(e.gn_out + 2 * (m / e.gn_rows) + 1, (double)sq);
     }
     if (e.act == ACT_GELU) {
 #pragma unroll
@@ -177,7 +200,13 @@ enum EpiKind {
     EK_GENERIC = 4,    // everything behind run-time flags            (tables, pixel shuffle, bf16 residual ...)
     EK_HEAD = 5,       // EPI_HEAD_FINAL                              (P2CL logits, 1-CTA BN=64 only)
     EK_BF16_TAB = 6,   // out bf16 = acc + table[m % rows]            (DMA image-side K|V|Q projection with the folded key_pe)
-    EK_PS = 7          // out bf16 = acc + bias, pixel-shuffle store  (ConvTranspose2d k=2 s=2 of the neck)
+    EK_PS = 7,         // out bf16 = acc + bias, pixel-shuffle store  (ConvTranspose2d k=2 s=2 of the neck)
+    // GroupNorm-fused neck variants (Epi::gn_*): the epilogue accumulates the per-sample sum / sum of squares of its
+    // fp32 outputs (so no statistics pass ever reads the tensor back), and EK_GNIN applies the producer's GroupNorm
+    // algebraically (no apply pass for the GroupNorms that are not followed by GELU)
+    EK_PS_ST = 8,      // EK_PS + statistics
+    EK_BF16_ST = 9,    // EK_BF16 + statistics
+    EK_GNIN_ST = 10    // out bf16 = rstd*acc - mean*rstd*wg + bias, + statistics
 };
 
 // measurement-only ablation (VPU_GEMM_ABLATE) is compiled in with -DVPU_GEMM_DEBUG: the check sat in the MMA issue loop
@@ -249,7 +278,22 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
         const bool out_bf16 = DYN ? (e.out_bf16 != 0) : (EK != EK_F32_RES);
         const int act = DYN ? e.act : (EK == EK_BF16_GELU ? ACT_GELU : (EK == EK_BF16_RELU ? ACT_RELU : ACT_NONE));
         const bool has_tab = DYN ? (e.bias2d != nullptr) : (EK == EK_BF16_TAB);
-        const bool pshuf = DYN ? (e.mode == EPI_PIXEL_SHUFFLE) : (EK == EK_PS);
+        const bool pshuf = DYN ? (e.mode == EPI_PIXEL_SHUFFLE) : (EK == EK_PS || EK == EK_PS_ST);
+        const bool stats = DYN ? (e.gn_out != nullptr) : (EK == EK_PS_ST || EK == EK_BF16_ST || EK == EK_GNIN_ST);
+        const bool gnin = DYN ? (e.gn_in != nullptr) : (EK == EK_GNIN_ST);
+        // a warp's 32 rows touch at most two samples (gn_rows >= 32): A = sample of the first row, B = the next one
+        float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f, rA = 1.f, mrA = 0.f, rB = 1.f, mrB = 0.f;
+        int mB = 0x7fffffff, sA = 0;
+        bool hasB = false;
+        if ((stats || gnin) && r_lo < d.M) {
+            sA = r_lo / e.gn_rows;
+            mB = (sA + 1) * e.gn_rows;
+            hasB = mB < d.M && mB < r_lo + 32;
+            if (gnin) {
+                gn_mean_rstd(e.gn_in, sA, e.gn_in_count, rA, mrA);
+                if (hasB) gn_mean_rstd(e.gn_in, sA + 1, e.gn_in_count, rB, mrB);
+            }
+        }
         const int sub = lane >> 3, j4 = (lane & 7) * 4;
         // rows of this lane are r_lo + sub + 4*it: the table row and the pixel-shuffle coordinates are divided out
         // once per tile and advanced by 4 per step (run-time divisions per row dominated these epilogues before)
@@ -267,8 +311,9 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
             tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
             const int n = n0 + j4;
             // operands that do not depend on the accumulator are requested while the TMEM load is in flight
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), wg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e.bias) bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+            if (gnin) wg = __ldg(reinterpret_cast<const float4*>(e.gn_wg + n));
             float4 res[8];
             if (has_res) {
 #pragma unroll
@@ -296,7 +341,17 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                 const int rr = 4 * it + sub, m = r_lo + rr;
                 float4 v = *reinterpret_cast<const float4*>(sbuf + rr * EPI_PITCH + j4);
                 if (m < d.M) {
+                    if (gnin) {
+                        const float r = m >= mB ? rB : rA, mr = m >= mB ? mrB : mrA;
+                        v.x = fmaf(v.x, r, -mr * wg.x); v.y = fmaf(v.y, r, -mr * wg.y);
+                        v.z = fmaf(v.z, r, -mr * wg.z); v.w = fmaf(v.w, r, -mr * wg.w);
+                    }
                     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    if (stats) {
+                        const float sm = (v.x + v.y) + (v.z + v.w);
+                        const float sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+                        if (m >= mB) { st_s1 += sm; st_q1 += sq; } else { st_s0 += sm; st_q0 += sq; }
+                    }
                     if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
                     if (has_tab) {
                         int trow = trow0 + 4 * it;                       // table rows >= 32 on this path: at most one wrap
@@ -325,6 +380,18 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                 }
             }
             __syncwarp();
+        }
+        if (stats) {
+            st_s0 = warp_sum(st_s0); st_q0 = warp_sum(st_q0);
+            st_s1 = warp_sum(st_s1); st_q1 = warp_sum(st_q1);
+            if (lane == 0 && r_lo < d.M) {
+                atomicAdd(e.gn_out + 2 * sA, (double)st_s0);
+                atomicAdd(e.gn_out + 2 * sA + 1, (double)st_q0);
+                if (hasB) {
+                    atomicAdd(e.gn_out + 2 * sA + 2, (double)st_s1);
+                    atomicAdd(e.gn_out + 2 * sA + 3, (double)st_q1);
+                }
+            }
         }
     }
 }
@@ -730,6 +797,9 @@ template <int BN> static int attrs2_all() {
     if (int rc = attr2<BN, EK_F32_RES>()) return rc;
     if (int rc = attr2<BN, EK_BF16_TAB>()) return rc;
     if (int rc = attr2<BN, EK_PS>()) return rc;
+    if (int rc = attr2<BN, EK_PS_ST>()) return rc;
+    if (int rc = attr2<BN, EK_BF16_ST>()) return rc;
+    if (int rc = attr2<BN, EK_GNIN_ST>()) return rc;
     return attr2<BN, EK_GENERIC>();
 }
 static int set_smem_attrs() {
@@ -843,6 +913,12 @@ static int launch_tc2_k(const GemmProblem& p, cudaStream_t stream) {
 
 // pick the compile-time epilogue the problem's run-time flags describe
 static int epi_kind(const Epi& e) {
+    if (e.gn_out || e.gn_in) {
+        const bool simple = e.out_bf16 && !e.res && !e.bias2d && e.act == ACT_NONE && e.bias && e.gn_out;
+        if (simple && e.mode == EPI_PIXEL_SHUFFLE && !e.gn_in && e.ps_g >= 8) return EK_PS_ST;
+        if (simple && e.mode == EPI_PLAIN) return e.gn_in ? EK_GNIN_ST : EK_BF16_ST;
+        return EK_GENERIC;
+    }
     if (e.mode == EPI_PIXEL_SHUFFLE && e.out_bf16 && !e.res && !e.bias2d && e.act == ACT_NONE && e.ps_g >= 8) return EK_PS;
     if (e.mode == EPI_PLAIN && e.bias2d && e.bias2d_rows >= 32 && e.out_bf16 && !e.res && e.act == ACT_NONE) return EK_BF16_TAB;
     if (e.mode != EPI_PLAIN || e.bias2d) return EK_GENERIC;
@@ -860,6 +936,9 @@ static int launch_tc2(const GemmProblem& p, cudaStream_t stream) {
         case EK_F32_RES: return launch_tc2_k<BN, EK_F32_RES>(p, stream);
         case EK_BF16_TAB: return launch_tc2_k<BN, EK_BF16_TAB>(p, stream);
         case EK_PS: return launch_tc2_k<BN, EK_PS>(p, stream);
+        case EK_PS_ST: return launch_tc2_k<BN, EK_PS_ST>(p, stream);
+        case EK_BF16_ST: return launch_tc2_k<BN, EK_BF16_ST>(p, stream);
+        case EK_GNIN_ST: return launch_tc2_k<BN, EK_GNIN_ST>(p, stream);
         default: return launch_tc2_k<BN, EK_GENERIC>(p, stream);
     }
 }
@@ -875,6 +954,11 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
     }
     if (p.epi.mode == EPI_PIXEL_SHUFFLE)
         VPU_REQUIRE(p.epi.ps_cout % 32 == 0 && p.N == 4 * p.epi.ps_cout, "pixel-shuffle GEMM needs N == 4*cout, cout %% 32 == 0");
+    if (p.epi.gn_out || p.epi.gn_in) {
+        VPU_REQUIRE(p.epi.gn_rows >= 32 && p.M % p.epi.gn_rows == 0, "GroupNorm-fused GEMM: gn_rows (%d) must be >= 32 and divide M", p.epi.gn_rows);
+        VPU_REQUIRE(!p.epi.gn_in || (p.epi.gn_wg && p.epi.gn_in_count > 0.f), "GroupNorm-fused GEMM: gn_in needs gn_wg and gn_in_count");
+        VPU_REQUIRE(p.epi.mode != EPI_HEAD_FINAL, "GroupNorm fusion is not available in the head-final epilogue");
+    }
     if (impl == 1) {
         GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
         dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);

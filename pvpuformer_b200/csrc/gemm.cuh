@@ -32,6 +32,16 @@ struct Epi {
     float* seg_out = nullptr;
     float seg_bias = 0.f;
     int nq = 0;
+    // GroupNorm(1, C) fusion for the neck (reference is_vpu_model.py:55-86; statistics over all values of one sample):
+    //   gn_out  [samples][2] doubles: += (sum, sum of squares) of this GEMM's fp32 outputs, per sample of gn_rows M-rows
+    //   gn_in   the same pair for the tensor the A operand holds un-normalised: the weights bound for this GEMM are
+    //           W' = W diag(gamma) and bias = W beta + b, so GN folds into  out = rstd * acc - mean * rstd * gn_wg[n] + bias[n]
+    //           with gn_wg[n] = sum_k W'[n, k]  (mean / rstd from gn_in over gn_in_count values, eps 1e-5)
+    double* gn_out = nullptr;
+    const double* gn_in = nullptr;
+    const float* gn_wg = nullptr;
+    int gn_rows = 0;
+    float gn_in_count = 0.f;
 };
 
 struct GemmProblem {

@@ -138,23 +138,27 @@ def pack_weights(sd, cfg, device):
         W(dst + ".w", f[src + ".weight"].reshape(f[src + ".weight"].shape[0], -1))
         F32(dst + ".b", f[src + ".bias"])
 
+    def conv1_gn(dst, src, gn):   # 1x1 conv applied to GroupNorm(1, C)(x) with x stored un-normalised (gemm.cuh Epi::gn_in):
+        w = f[src + ".weight"].reshape(f[src + ".weight"].shape[0], -1)      # W (gamma (x - mean) rstd + beta) + b
+        wq = (w * f[gn + ".weight"].view(1, -1)).to(bf)                       #   = rstd (W' x) - mean rstd rowsum(W') + (W beta + b)
+        out[dst + ".w"] = wq.contiguous()
+        F32(dst + ".wg", wq.float().sum(dim=1))                               # row sums of the ROUNDED W': consistent with the MMA
+        F32(dst + ".b", w @ f[gn + ".bias"] + f[src + ".bias"])
+
     convT("d4.a", "neck.down_4.0")
     norm("d4.gn1", "neck.down_4.1")
     convT("d4.b", "neck.down_4.3")
-    norm("d4.gn2", "neck.down_4.4")
-    conv1("d4.c", "neck.down_4.5")
+    conv1_gn("d4.c", "neck.down_4.5", "neck.down_4.4")
     norm("d4.gn3", "neck.down_4.6")
     convT("d8.a", "neck.down_8.0")
-    norm("d8.gn1", "neck.down_8.1")
-    conv1("d8.b", "neck.down_8.2")
+    conv1_gn("d8.b", "neck.down_8.2", "neck.down_8.1")
     norm("d8.gn2", "neck.down_8.3")
     conv1("d16.a", "neck.down_16.0")
     norm("d16.gn1", "neck.down_16.1")
     w = f["neck.down_32.0.weight"]                                # [cout, C, 2, 2] -> [cout, (kh,kw,C)]
     W("d32.a.w", w.permute(0, 2, 3, 1).reshape(w.shape[0], 4 * C))
     F32("d32.a.b", f["neck.down_32.0.bias"])
-    norm("d32.gn1", "neck.down_32.1")
-    conv1("d32.b", "neck.down_32.2")
+    conv1_gn("d32.b", "neck.down_32.2", "neck.down_32.1")
     norm("d32.gn2", "neck.down_32.3")
 
     # ---- head ----
