@@ -297,6 +297,9 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     const int heads = h.d.num_heads, hd = C / heads;
     typedef __nv_bfloat16 bf;
 
+    // GroupNorm accumulators of the neck: cleared here so that no memset node sits between two kernels later on
+    // (a non-kernel node would break the programmatic-dependent-launch chain, common.cuh)
+    VPU_CHECK_CUDA(cudaMemsetAsync(f.buf<double>("gn_sums"), 0, (size_t)8 * B * 2 * sizeof(double), s));
     // ---- A1-A3, A7: fused image + coord-feature patch operand, one GEMM for both patch embeds ----
     CoordArgs ca;
     ca.image4 = image4; ca.points = pr.points; ca.extra_mask = pr.extra_mask; ca.n = pr.n; ca.H = img; ca.W = img;
@@ -437,8 +440,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     // GroupNorm(1, C) is fused into the GEMMs on both sides (Epi::gn_*): every GEMM accumulates the per-sample sum / sum of
     // squares of its fp32 outputs in its epilogue, the three GroupNorms that are not followed by GELU (d4.gn2, d8.gn1,
     // d32.gn1) are folded into the consuming 1x1 conv, and the other five need one apply (+GELU) pass and no statistics pass.
-    double* sums = f.buf<double>("gn_sums");
-    VPU_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)8 * B * 2 * sizeof(double), s));
+    double* sums = f.buf<double>("gn_sums");     // zeroed at the top of the forward
     auto S = [&](int i) { return sums + (size_t)i * B * 2; };
     typedef Fwd::Gn Gn;
     Gn gn;

@@ -53,6 +53,8 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int PITCH = D + 8;            // +16 B per row: conflict-free ldmatrix
     constexpr int CHUNKS = D / 8;           // 16-byte chunks per row
     extern __shared__ __align__(16) uint8_t att_smem[];
@@ -219,7 +221,7 @@ static int launch_att(const AttnArgs& a, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid((a.Sq + ATT_BM - 1) / ATT_BM, a.heads, a.nprob);
-    attention_kernel<D><<<grid, ATT_THREADS, smem, stream>>>(a);
+    VPU_CHECK_CUDA(launch_pdl(attention_kernel<D>, dim3(grid), dim3(ATT_THREADS), smem, stream, a));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -115,6 +115,7 @@ struct WinArgs {
 __global__ void __launch_bounds__(THREADS, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ0,
                            const __grid_constant__ CUtensorMap tmQ1, const WinArgs a) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], s_full[2], p_full[2], o_full[2], s_empty[2];
     __shared__ uint32_t tmem_base_smem;
@@ -155,6 +156,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();     // the set-up above overlapped the tail of the previous kernel; global memory is touched only below
     const int nw2 = a.nwin_side * a.nwin_side;
 
     if (warp == 0) {
@@ -429,6 +431,7 @@ struct GlobArgs {
 __global__ void __launch_bounds__(G_THREADS, 1)
 global_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, const GlobArgs a) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t q_full[2], q_empty[2], kv_full[G_STAGES], kv_empty[G_STAGES], s_full[2], s_free[2], p_full[2], pv_done[2];
     __shared__ uint32_t tmem_base_smem;
@@ -466,6 +469,7 @@ global_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();     // the set-up above overlapped the tail of the previous kernel; global memory is touched only below
     const int last_tile_pair = a.npairs - 1;
     const bool odd_tiles = (a.ntiles & 1) != 0;      // the last pair of every problem holds a single tile
 
@@ -855,7 +859,7 @@ int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
     g.ablate = ablate;
     g.trace = g_trace; g.trace_cap = g_trace_cap;
     const int ctas = g.nunits < g_sms ? g.nunits : g_sms;
-    global_attention_tc_kernel<<<ctas, G_THREADS, G_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, g);
+    VPU_CHECK_CUDA(launch_pdl(global_attention_tc_kernel, dim3(ctas), dim3(G_THREADS), G_SMEM_BYTES, stream, tmQ, tmK, tmV, g));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -880,7 +884,7 @@ int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
     w.o = a.o; w.ldo = a.ldo; w.heads = a.heads; w.nwin_side = nws; w.grid = grid; w.tokens = a.qmap.tokens;
     w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
     const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
-    window_attention_tc_kernel<<<ctas, THREADS, SMEM_BYTES, stream>>>(tmKV, tmQ0, tmQ1, w);
+    VPU_CHECK_CUDA(launch_pdl(window_attention_tc_kernel, dim3(ctas), dim3(THREADS), SMEM_BYTES, stream, tmKV, tmQ0, tmQ1, w));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -29,7 +29,18 @@ unsigned long long launch_count();
         }                                 \
     } while (0)
 
+bool pdl_enabled();      // VPU_PDL=1 switches the launch attribute on (off by default, see gemm.cu)
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // ---- small math / packing -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -40,6 +51,37 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
     return __bfloat1622float2(v);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (reference nn.GELU(), models_vit.py:14-27) evaluated as x * Phi(x) with
+// Phi(x) = 0.5 (1 + tanh(u)) = 1 / (1 + exp(-2u)), u = x (a + b x^2 + c x^4), (a, b, c) a minimax fit of the erf form:
+// |gelu(x) - x Phi(x)| <= 2.6e-5 for every x (the fit is exact to O(x^3) at 0).  ex2.approx + rcp.approx keep the
+// evaluation error at ~1e-6 (tanh.approx's 2^-11 relative error moved the stress-weights parity test), so the total
+// stays below the half-ulp of the bf16 this epilogue stores.  7 FMA-pipe instructions + two MUFUs per element: the
+// previous Abramowitz-Stegun erf (19 instructions + MUFU) made the fc1 epilogue (32768 elements per CTA tile) longer
+// than the tile's MMA time (A/B on B200, fc1 M=50176: 243 us -> 218 us).
+#ifdef VPU_GELU_AS   // A/B build only: the previous Abramowitz-Stegun 7.1.28 erf (|error| <= 3e-7, 19 instructions + MUFU)
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float p = 0.0000430638f;
+    p = fmaf(p, z, 0.0002765672f); p = fmaf(p, z, 0.0001520143f); p = fmaf(p, z, 0.0092705272f);
+    p = fmaf(p, z, 0.0422820123f); p = fmaf(p, z, 0.0705230784f); p = fmaf(p, z, 1.0f);
+    p = p * p; p = p * p; p = p * p; p = p * p;
+    float rp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rp) : "f"(p));
+    const float h = 0.5f * x;
+    return fmaf(h, copysignf(1.0f - rp, x), h);
+}
+#else
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float x2 = fminf(x * x, 64.0f);   // the quartic turns over at |x| = 11; Phi is saturated (|u| >= 13.8) from |x| = 8
+    // -2 log2(e) * (a, b, c): v = -2 u log2(e)
+    float t = fmaf(1.014263054e-3f, x2, -1.067757239e-1f);
+    t = fmaf(t, x2, -2.301121339f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));     // e = +inf (x << 0) -> r = 0
+    return x * r;
+}
+#endif
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -93,6 +135,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();
     }
 }
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// With VPU_PDL=1 every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl),
+// calls pdl_launch_dependents() first thing -- so the next kernel of the stream may be scheduled while this one runs --
+// and pdl_wait() before it reads or writes global memory: griddepcontrol.wait returns once the preceding kernel has
+// completed and its writes are visible, so the semantics stay those of a serialised stream, minus the launch latency
+// and the prologue (barrier init, TMEM allocation, descriptor prefetch) of ~185 kernels per forward.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // One lane of the (converged) warp.  Issue code for TMA / tcgen05 belongs under `if (elect_one())` in a warp that runs its
 // loop converged, NOT under `if (lane == 0)`: there nvcc cannot prove single-lane execution and wraps every uniform-datapath

@@ -12,6 +12,8 @@ namespace vpu {
 // ------------------------------------------------------------------------------------------
 template <int VEC>  // C = 128 * VEC
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= a.rows) return;
     constexpr int C = 128 * VEC;
@@ -64,9 +66,9 @@ int layernorm_launch(const LnArgs& a, int C, cudaStream_t stream) {
     VPU_REQUIRE(a.rows > 0, "layernorm: no rows");
     const int grid = (a.rows + 7) / 8;
     switch (C) {
-        case 768: layernorm_kernel<6><<<grid, 256, 0, stream>>>(a); break;
-        case 1024: layernorm_kernel<8><<<grid, 256, 0, stream>>>(a); break;
-        case 1280: layernorm_kernel<10><<<grid, 256, 0, stream>>>(a); break;
+        case 768: VPU_CHECK_CUDA(launch_pdl(layernorm_kernel<6>, dim3(grid), dim3(256), 0, stream, a)); break;
+        case 1024: VPU_CHECK_CUDA(launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, stream, a)); break;
+        case 1280: VPU_CHECK_CUDA(launch_pdl(layernorm_kernel<10>, dim3(grid), dim3(256), 0, stream, a)); break;
         default: VPU_REQUIRE(false, "layernorm: unsupported width %d (768/1024/1280)", C);
     }
     VPU_CHECK_CUDA(cudaGetLastError());
@@ -77,6 +79,8 @@ int layernorm_launch(const LnArgs& a, int C, cudaStream_t stream) {
 // out_bf16 = bf16(a (+ b)); n multiple of 4
 __global__ void __launch_bounds__(256) cast_add_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                        __nv_bfloat16* __restrict__ out, size_t n4) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 x = reinterpret_cast<const float4*>(a)[i];
         if (b) {
@@ -91,7 +95,7 @@ int cast_add_launch(const float* a, const float* b, __nv_bfloat16* out, size_t n
     const size_t n4 = n / 4;
     int grid = (int)((n4 + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    cast_add_kernel<<<grid, 256, 0, stream>>>(a, b, out, n4);
+    VPU_CHECK_CUDA(launch_pdl(cast_add_kernel, dim3(grid), dim3(256), 0, stream, a, b, out, n4));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -104,6 +108,8 @@ int cast_add_launch(const float* a, const float* b, __nv_bfloat16* out, size_t n
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, size_t per_sample,
                                                        float2* __restrict__ partial) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, chunks = gridDim.x;
     const uint4* p = reinterpret_cast<const uint4*>(x + (size_t)b * per_sample);
     const size_t n8 = per_sample / 8;
@@ -127,6 +133,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
 }
 __global__ void gn_finalize_kernel(const float2* __restrict__ partial, int chunks, double count, float eps,
                                    float2* __restrict__ mean_rstd) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     double s = 0.0, ss = 0.0;
     for (int i = threadIdx.x; i < chunks; i += 32) { s += partial[(size_t)b * chunks + i].x; ss += partial[(size_t)b * chunks + i].y; }
@@ -143,6 +151,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
                                                        const float2* __restrict__ mean_rstd, const double* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int gelu) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, C8 = C / 8, C8z = C8 / gridDim.z;      // wide layers split their channels over grid.z
     const int co = blockIdx.z * C8z + threadIdx.x % C8z, prow = threadIdx.x / C8z, rows_per_block = blockDim.x / C8z;
     float2 mr;
@@ -163,10 +173,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
         for (int k = 0; k < 8; ++k) { sc[k] = mr.y * g[k]; sh[k] = bb[k] - mr.x * mr.y * g[k]; }   // y = x*sc + sh
     }
     uint4* p = reinterpret_cast<uint4*>(x + (size_t)b * per_sample);
-    const size_t npix = per_sample / C;
-    for (size_t pix = (size_t)blockIdx.x * rows_per_block + prow; pix < npix; pix += (size_t)gridDim.x * rows_per_block) {
-        const size_t i = pix * C8 + co;
-        uint4 v = p[i];
+    const size_t npix = per_sample / C, step = (size_t)gridDim.x * rows_per_block;
+    auto apply = [&](uint4 v) {
         float f[8];
         float2 t;
         t = unpack_bf16(v.x); f[0] = t.x; f[1] = t.y;
@@ -176,28 +184,38 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float y = fmaf(f[k], sc[k], sh[k]);
-            f[k] = gelu ? gelu_erf(y) : y;
+            f[k] = gelu ? gelu_fast(y) : y;
         }
-        v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]); v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
-        p[i] = v;
+        return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    };
+    // four pixels per iteration: the four 16-byte loads are in flight together (one load per iteration left the kernel
+    // latency-bound at 2.4 TB/s)
+    size_t pix = (size_t)blockIdx.x * rows_per_block + prow;
+    for (; pix + 3 * step < npix; pix += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p[(pix + u * step) * C8 + co];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[(pix + u * step) * C8 + co] = apply(v[u]);
     }
+    for (; pix < npix; pix += step) p[pix * C8 + co] = apply(p[pix * C8 + co]);
 }
 int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta,
                      int gelu, float2* partial, float2* mean_rstd, cudaStream_t stream) {
     VPU_REQUIRE(per_sample % 8 == 0 && C % 8 == 0, "groupnorm: sizes must be multiples of 8");
     int chunks = (int)((per_sample / 8 + 255) / 256);
     if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-    gn_stats_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, per_sample, partial);
-    gn_finalize_kernel<<<B, 32, 0, stream>>>(partial, chunks, (double)per_sample, 1e-5f, mean_rstd);
+    VPU_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(256), 0, stream, x, per_sample, partial));
+    VPU_CHECK_CUDA(launch_pdl(gn_finalize_kernel, dim3(B), dim3(32), 0, stream, partial, chunks, (double)per_sample, 1e-5f, mean_rstd));
     VPU_REQUIRE(per_sample % C == 0, "groupnorm: C must divide the sample size");
     const int C8 = C / 8;
     int zsplit = 1;
     while (C8 / zsplit > 256 || C8 % zsplit) ++zsplit;
     const int C8z = C8 / zsplit, threads = C8z * (256 / C8z);
     const size_t npix = per_sample / C;
-    int blocks = (int)((npix + (threads / C8z) - 1) / (threads / C8z));
+    int blocks = (int)((npix + 4 * (threads / C8z) - 1) / (4 * (threads / C8z)));     // four pixels per thread
     if (blocks > 148 * 8) blocks = 148 * 8;
-    gn_apply_kernel<<<dim3(blocks, B, zsplit), threads, 0, stream>>>(x, per_sample, C, mean_rstd, nullptr, gamma, beta, gelu);
+    VPU_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks, B, zsplit), dim3(threads), 0, stream, x, per_sample, C, mean_rstd, nullptr, gamma, beta, gelu));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch(3);
     return 0;
@@ -212,9 +230,9 @@ int groupnorm_apply_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, co
     while (C8 / zsplit > 256 || C8 % zsplit) ++zsplit;
     const int C8z = C8 / zsplit, threads = C8z * (256 / C8z);
     const size_t npix = per_sample / C;
-    int blocks = (int)((npix + (threads / C8z) - 1) / (threads / C8z));
+    int blocks = (int)((npix + 4 * (threads / C8z) - 1) / (4 * (threads / C8z)));     // four pixels per thread
     if (blocks > 148 * 8) blocks = 148 * 8;
-    gn_apply_kernel<<<dim3(blocks, B, zsplit), threads, 0, stream>>>(x, per_sample, C, nullptr, sums, gamma, beta, gelu);
+    VPU_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks, B, zsplit), dim3(threads), 0, stream, x, per_sample, C, nullptr, sums, gamma, beta, gelu));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -228,6 +246,8 @@ __global__ void __launch_bounds__(128) qout_gate_kernel(const float* __restrict_
                                                         const float* __restrict__ q2, const float* __restrict__ q3,
                                                         int T, int C, float* __restrict__ qout,
                                                         __nv_bfloat16* __restrict__ qout_bf16, float* __restrict__ cg) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x, B = gridDim.y;
     if (c >= C) return;
     float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -245,7 +265,7 @@ __global__ void __launch_bounds__(128) qout_gate_kernel(const float* __restrict_
 }
 int qout_gate_launch(const float* q0, const float* q1, const float* q2, const float* q3, int B, int T, int C, float* qout,
                      __nv_bfloat16* qout_bf16, float* cg, cudaStream_t stream) {
-    qout_gate_kernel<<<dim3((C + 127) / 128, B), 128, 0, stream>>>(q0, q1, q2, q3, T, C, qout, qout_bf16, cg);
+    VPU_CHECK_CUDA(launch_pdl(qout_gate_kernel, dim3((C + 127) / 128, B), dim3(128), 0, stream, q0, q1, q2, q3, T, C, qout, qout_bf16, cg));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -257,6 +277,8 @@ int qout_gate_launch(const float* q0, const float* q1, const float* q2, const fl
 // x4 in the space-to-depth layout the 2x2/stride-2 conv of down_32 consumes as a plain GEMM.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C4 = a.C / 4;
     const size_t total = (size_t)a.M * C4;
     const int g = a.grid, gh = g / 2;
@@ -286,7 +308,7 @@ int merge_launch(const MergeArgs& a, cudaStream_t stream) {
     const size_t total = (size_t)a.M * (a.C / 4);
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    merge_kernel<<<grid, 256, 0, stream>>>(a);
+    VPU_CHECK_CUDA(launch_pdl(merge_kernel, dim3(grid), dim3(256), 0, stream, a));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -316,52 +338,63 @@ __device__ __forceinline__ void acc8(float (&f)[8], const __nv_bfloat16* p, floa
     t = unpack_bf16(v.z); f[4] += w * t.x; f[5] += w * t.y;
     t = unpack_bf16(v.w); f[6] += w * t.x; f[7] += w * t.y;
 }
-// one warp per output pixel, 256 channels = 8 per lane
+// 256 channels = 8 per lane, one warp per output pixel at a time.  A block owns an 8 x 8 patch of output pixels (warp w =
+// row w of the patch, 8 pixels in sequence), so the 2 x 2 bilinear taps of the three coarser levels -- 12 of the 13
+// 512-byte loads per pixel -- are shared through L1 by the whole patch (6x6 / 4x4 / 3x3 source pixels per 64 outputs).
+// With one pixel row of 8 per block (round 1c) every tap came from L2: 5.3 GB of L2 traffic for 0.96 GB of HBM bytes.
 __global__ void __launch_bounds__(256) head_combine_kernel(const HeadCombineArgs a) {
-    const size_t pix = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    const int R = a.res[0];
-    if (pix >= (size_t)a.B * R * R) return;
-    const int b = (int)(pix / ((size_t)R * R)), yx = (int)(pix % ((size_t)R * R)), y = yx / R, x = yx % R;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int R = a.res[0], T = R / 8;
+    const int b = blockIdx.x / (T * T), tyx = blockIdx.x % (T * T), y = (tyx / T) * 8 + warp, xb = (tyx % T) * 8;
     const int c = lane * 8;
-    float f[8];
-    {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
-        f[0] = b0.x; f[1] = b0.y; f[2] = b0.z; f[3] = b0.w; f[4] = b1.x; f[5] = b1.y; f[6] = b1.z; f[7] = b1.w;
-    }
-    acc8(f, a.y[0] + pix * 256 + c, 1.0f);
-#pragma unroll
-    for (int l = 1; l < 4; ++l) {
-        const int r = a.res[l];
-        int y0, y1, x0, x1;
-        float ly, lx;
-        src_index(y, r, R, y0, y1, ly);
-        src_index(x, r, R, x0, x1, lx);
-        const __nv_bfloat16* base = a.y[l] + (size_t)b * r * r * 256 + c;
-        acc8(f, base + ((size_t)y0 * r + x0) * 256, (1.f - ly) * (1.f - lx));
-        acc8(f, base + ((size_t)y0 * r + x1) * 256, (1.f - ly) * lx);
-        acc8(f, base + ((size_t)y1 * r + x0) * 256, ly * (1.f - lx));
-        acc8(f, base + ((size_t)y1 * r + x1) * 256, ly * lx);
-    }
-    float ss = 0.f, seg = 0.f;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.wseg + c)), w1 = __ldg(reinterpret_cast<const float4*>(a.wseg + c + 4));
     const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    int y0[4], y1[4];
+    float ly[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        f[k] = fmaxf(f[k], 0.f);
-        ss += f[k] * f[k];
-        seg += f[k] * ws[k];                     // conv_seg (decode_head.py:210-215) in fp32, before the bf16 store
+    for (int l = 1; l < 4; ++l) src_index(y, a.res[l], R, y0[l], y1[l], ly[l]);
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+        const int x = xb + i;
+        const size_t pix = ((size_t)b * R + y) * R + x;
+        float f[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        acc8(f, a.y[0] + pix * 256 + c, 1.0f);
+#pragma unroll
+        for (int l = 1; l < 4; ++l) {
+            const int r = a.res[l];
+            int x0, x1;
+            float lx;
+            src_index(x, r, R, x0, x1, lx);
+            const __nv_bfloat16* base = a.y[l] + (size_t)b * r * r * 256 + c;
+            acc8(f, base + ((size_t)y0[l] * r + x0) * 256, (1.f - ly[l]) * (1.f - lx));
+            acc8(f, base + ((size_t)y0[l] * r + x1) * 256, (1.f - ly[l]) * lx);
+            acc8(f, base + ((size_t)y1[l] * r + x0) * 256, ly[l] * (1.f - lx));
+            acc8(f, base + ((size_t)y1[l] * r + x1) * 256, ly[l] * lx);
+        }
+        float ss = 0.f, seg = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            f[k] = fmaxf(f[k], 0.f);
+            ss += f[k] * f[k];
+            seg += f[k] * ws[k];                     // conv_seg (decode_head.py:210-215) in fp32, before the bf16 store
+        }
+        ss = warp_sum(ss);
+        seg = warp_sum(seg);
+        *reinterpret_cast<uint4*>(a.out + pix * 256 + c) =
+            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        if (lane == 0) {
+            a.seg_out[pix] = seg + a.seg_bias;
+            a.rnorm[pix] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        }
     }
-    ss = warp_sum(ss);
-    seg = warp_sum(seg);
-    if (lane == 0) a.seg_out[pix] = seg + a.seg_bias;
-    *reinterpret_cast<uint4*>(a.out + pix * 256 + c) =
-        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-    if (lane == 0) a.rnorm[pix] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 }
 int head_combine_launch(const HeadCombineArgs& a, cudaStream_t stream) {
-    const size_t npix = (size_t)a.B * a.res[0] * a.res[0];
-    head_combine_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, stream>>>(a);
+    VPU_REQUIRE(a.res[0] % 8 == 0, "head combine: the 1/4-scale resolution (%d) must be a multiple of 8", a.res[0]);
+    const int T = a.res[0] / 8;
+    VPU_CHECK_CUDA(launch_pdl(head_combine_kernel, dim3((unsigned)(a.B * T * T)), dim3(256), 0, stream, a));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -372,6 +405,8 @@ int head_combine_launch(const HeadCombineArgs& a, cudaStream_t stream) {
 // queries, row nq = conv_seg weight, remaining rows zero.
 __global__ void __launch_bounds__(256) head_queries_kernel(const float* __restrict__ qe, const float* __restrict__ wseg,
                                                            int nq, __nv_bfloat16* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x, r = blockIdx.y, c = threadIdx.x;  // 256 channels
     __shared__ float sh[8];
     float v = 0.f, scale = 1.f;
@@ -390,7 +425,7 @@ __global__ void __launch_bounds__(256) head_queries_kernel(const float* __restri
 }
 int head_queries_launch(const float* qe, const float* wseg, int B, int nq, __nv_bfloat16* out, cudaStream_t stream) {
     VPU_REQUIRE(nq < 64, "head queries: nq must be < 64");
-    head_queries_kernel<<<dim3(B, 64), 256, 0, stream>>>(qe, wseg, nq, out);
+    VPU_CHECK_CUDA(launch_pdl(head_queries_kernel, dim3(B, 64), dim3(256), 0, stream, qe, wseg, nq, out));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -402,6 +437,8 @@ int head_queries_launch(const float* qe, const float* wseg, int B, int nq, __nv_
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
                                                           int H, int W, size_t planes) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int W4 = W / 4;
     const size_t total = planes * H * W4;
     const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
@@ -431,6 +468,8 @@ __global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restric
 // 3 x 3 source patch, so loads drop from 64 to 9 per block and the horizontal interpolation is shared by 4 rows.
 __global__ void __launch_bounds__(256) upsample_ac4_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
                                                            int H, int W, size_t planes) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int W4 = W / 4, H4 = H / 4;
     const size_t total = planes * H4 * W4;
     const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
@@ -484,7 +523,7 @@ int upsample_ac_launch(const float* in, float* out, int h, int w, int H, int W, 
         const size_t total = planes * (H / 4) * (W / 4);
         size_t grid = (total + 255) / 256;
         if (grid > 148 * 32) grid = 148 * 32;
-        upsample_ac4_kernel<<<(unsigned)grid, 256, 0, stream>>>(in, out, h, w, H, W, planes);
+        VPU_CHECK_CUDA(launch_pdl(upsample_ac4_kernel, dim3((unsigned)grid), dim3(256), 0, stream, in, out, h, w, H, W, planes));
         VPU_CHECK_CUDA(cudaGetLastError());
         count_launch();
         return 0;
@@ -492,7 +531,7 @@ int upsample_ac_launch(const float* in, float* out, int h, int w, int H, int W, 
     const size_t total = planes * H * (W / 4);
     size_t grid = (total + 255) / 256;
     if (grid > 148 * 32) grid = 148 * 32;
-    upsample_ac_kernel<<<(unsigned)grid, 256, 0, stream>>>(in, out, h, w, H, W, planes);
+    VPU_CHECK_CUDA(launch_pdl(upsample_ac_kernel, dim3((unsigned)grid), dim3(256), 0, stream, in, out, h, w, H, W, planes));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;

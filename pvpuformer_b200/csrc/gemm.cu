@@ -30,6 +30,13 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+bool pdl_enabled() {
+    // off by default: on the power-capped (~400 W) B200s of this pool closing the inter-kernel gaps lowered the SM clock
+    // by as much as it saved (A/B, batch-64 ViT-B step: 16.54 ms at 1620 MHz with PDL, 16.15 ms at 1725 MHz without)
+    static const bool on = [] { const char* e = getenv("VPU_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
@@ -220,38 +227,6 @@ constexpr int EPI_PITCH = 36;                        // fp32 words per staged ro
 constexpr int EPI_WARP_WORDS = 32 * EPI_PITCH;       // 4608 B per epilogue warp
 constexpr int EPI_SMEM_BYTES = 8 * EPI_WARP_WORDS * 4;
 
-// erf-GELU (reference nn.GELU(), models_vit.py:14-27) evaluated as x * Phi(x) with
-// Phi(x) = 0.5 (1 + tanh(u)) = 1 / (1 + exp(-2u)), u = x (a + b x^2 + c x^4), (a, b, c) a minimax fit of the erf form:
-// |gelu(x) - x Phi(x)| <= 2.6e-5 for every x (the fit is exact to O(x^3) at 0).  ex2.approx + rcp.approx keep the
-// evaluation error at ~1e-6 (tanh.approx's 2^-11 relative error moved the stress-weights parity test), so the total
-// stays below the half-ulp of the bf16 this epilogue stores.  7 FMA-pipe instructions + two MUFUs per element: the
-// previous Abramowitz-Stegun erf (19 instructions + MUFU) made the fc1 epilogue (32768 elements per CTA tile) longer
-// than the tile's MMA time (A/B on B200, fc1 M=50176: 243 us -> 218 us).
-#ifdef VPU_GELU_AS   // A/B build only: the previous Abramowitz-Stegun 7.1.28 erf (|error| <= 3e-7, 19 instructions + MUFU)
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    float p = 0.0000430638f;
-    p = fmaf(p, z, 0.0002765672f); p = fmaf(p, z, 0.0001520143f); p = fmaf(p, z, 0.0092705272f);
-    p = fmaf(p, z, 0.0422820123f); p = fmaf(p, z, 0.0705230784f); p = fmaf(p, z, 1.0f);
-    p = p * p; p = p * p; p = p * p; p = p * p;
-    float rp;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rp) : "f"(p));
-    const float h = 0.5f * x;
-    return fmaf(h, copysignf(1.0f - rp, x), h);
-}
-#else
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float x2 = fminf(x * x, 64.0f);   // the quartic turns over at |x| = 11; Phi is saturated (|u| >= 13.8) from |x| = 8
-    // -2 log2(e) * (a, b, c): v = -2 u log2(e)
-    float t = fmaf(1.014263054e-3f, x2, -1.067757239e-1f);
-    t = fmaf(t, x2, -2.301121339f);
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * t));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));     // e = +inf (x << 0) -> r = 0
-    return x * r;
-}
-#endif
-
 template <int BN, int EK>
 __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, uint32_t tmem_acc, int row_base, int col_base,
                                               int quarter, int half, int lane, float* sbuf) {
@@ -418,6 +393,7 @@ template <int BN, int EK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDims d,
                const Epi e) {
+    pdl_launch_dependents();
     using C = TileCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], tfull_bar[2], tempty_bar[2];
@@ -448,6 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();     // everything above overlapped the tail of the previous kernel; global memory is touched only below
 
     const int n_blks = (d.N + BN - 1) / BN;
     const int m_blks = (d.M + BM - 1) / BM;
@@ -554,6 +531,7 @@ template <int BN, int EK, int CL>   // CL = CTAs per cluster: 2 (one MMA pair) o
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDims d,
                 const Epi e) {
+    pdl_launch_dependents();
     using C = TileCfg2<BN>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], tfull_bar[2], tempty_bar[2];
@@ -589,6 +567,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();     // barriers of both CTAs initialised before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();     // everything above overlapped the tail of the previous kernel; global memory is touched only below
 
     const int n_blks = (d.N + BN - 1) / BN;
     const int m_blks = (d.M + 2 * BM * PP - 1) / (2 * BM * PP);     // cluster tiles along M: PP * 256 rows each
@@ -698,6 +677,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 __global__ void __launch_bounds__(128) gemm_mma_kernel(const __nv_bfloat16* __restrict__ A,
                                                        const __nv_bfloat16* __restrict__ W, int lda, int ldw,
                                                        const GemmDims d, const Epi e) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(16) __nv_bfloat16 As[64][40];
     __shared__ __align__(16) __nv_bfloat16 Bs[64][40];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -870,7 +851,7 @@ static int launch_tc(const GemmProblem& p, cudaStream_t stream) {
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
-    gemm_tc_kernel<BN, EK><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d, p.epi);
+    VPU_CHECK_CUDA(launch_pdl(gemm_tc_kernel<BN, EK>, dim3(grid), dim3(GEMM_THREADS), TileCfg<BN>::SMEM_BYTES, stream, tmA, tmB, d, p.epi));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -884,10 +865,12 @@ static int launch_tc2_cl(const GemmProblem& p, cudaStream_t stream) {
     if (int rc = make_tmap(&tmB, p.W, p.w_rows ? p.w_rows : p.N, p.K, p.ldw, BN / 2 / PP)) return rc;
     const int tiles = ((p.M + 2 * BM * PP - 1) / (2 * BM * PP)) * ((p.N + BN - 1) / BN);
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = TileCfg2<BN>::SMEM_BYTES; cfg.stream = stream;
     static int max_clusters = 0;      // co-resident clusters of this instantiation (a persistent grid must not exceed it by much)
     if (max_clusters == 0) {
@@ -963,7 +946,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
         dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
         if (p.epi.m_per_batch > 0) VPU_REQUIRE(p.epi.m_per_batch % 64 == 0, "m_per_batch must be a multiple of 64");
-        gemm_mma_kernel<<<grid, 128, 0, stream>>>(p.A, p.W, p.lda, p.ldw, d, p.epi);
+        VPU_CHECK_CUDA(launch_pdl(gemm_mma_kernel, dim3(grid), dim3(128), 0, stream, p.A, p.W, p.lda, p.ldw, d, p.epi));
         VPU_CHECK_CUDA(cudaGetLastError());
         count_launch();
         return 0;

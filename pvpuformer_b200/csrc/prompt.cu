@@ -21,6 +21,8 @@ __device__ __forceinline__ bool in_img(int x, int y, int w, int h) {  // ops.py:
 
 // One CTA per output row (b, j).  Row = [vec_a(S) | vec_b(S) | label(3)].
 __global__ void __launch_bounds__(128) ppue_kernel(const PpueArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.x, b = blockIdx.y;
     const int S = a.size, D = 2 * S + 3, n = a.n, NM = a.num_max_points;
     const int half = j / NM, slot = j % NM;
@@ -100,7 +102,7 @@ int ppue_launch(const PpueArgs& a, int B, cudaStream_t stream) {
                 "PPuE: prompt type %d needs its side inputs", a.type);
     VPU_REQUIRE(a.click_radius >= 0 && 2 * a.click_radius + 1 <= 32, "PPuE: click table too large");
     dim3 grid(2 * a.num_max_points, B);
-    ppue_kernel<<<grid, 128, 0, stream>>>(a);
+    VPU_CHECK_CUDA(launch_pdl(ppue_kernel, dim3(grid), dim3(128), 0, stream, a));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -141,6 +143,8 @@ __device__ __forceinline__ bool disk_hit(const SmemPoints& sp, int h, int r, int
 
 // grid (H, B), block 256: one image row per CTA.
 __global__ void __launch_bounds__(256) coord_features_kernel(const CoordArgs a, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ SmemPoints sp;
     const int y = blockIdx.x, b = blockIdx.y, H = a.H, W = a.W;
     load_points(sp, a.points + (size_t)b * 2 * a.n * 3, a.n);
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(256) coord_features_kernel(const CoordArgs a, 
 int coord_features_launch(const CoordArgs& a, int B, float* out, cudaStream_t stream) {
     VPU_REQUIRE(a.n >= 1 && a.n <= 24, "coord features: n=%d outside [1, 24]", a.n);
     dim3 grid(a.H, B);
-    coord_features_kernel<<<grid, 256, 0, stream>>>(a, out);
+    VPU_CHECK_CUDA(launch_pdl(coord_features_kernel, dim3(grid), dim3(256), 0, stream, a, out));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -174,6 +178,8 @@ int coord_features_launch(const CoordArgs& a, int B, float* out, cudaStream_t st
 // planes 6..9: the bf16 "lo" residuals of R, G, B, prev mask ({0,1} disks are exact).  Row = 10*p*p.
 __global__ void __launch_bounds__(256) patch_operand_kernel(const CoordArgs a, __nv_bfloat16* __restrict__ A, int p,
                                                             int lda) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ SmemPoints sp;
     const int y = blockIdx.x, b = blockIdx.y, H = a.H, W = a.W;
     load_points(sp, a.points + (size_t)b * 2 * a.n * 3, a.n);
@@ -211,7 +217,7 @@ int patch_operand_launch(const CoordArgs& a, int B, __nv_bfloat16* A, int patch,
     dim3 grid(a.H, B);
     int threads = a.W / 2;
     threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;
-    patch_operand_kernel<<<grid, threads, 0, stream>>>(a, A, patch, lda);
+    VPU_CHECK_CUDA(launch_pdl(patch_operand_kernel, dim3(grid), dim3(threads), 0, stream, a, A, patch, lda));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
