@@ -305,11 +305,20 @@ def main():
         return (sum(c["flops"] for c in cs) / (t * 1e-3) / 1e12) if t > 0 else 0.0
 
     g_tf = tf(gemm)
+    # DRAM bytes per launch of the GEMM class from the committed ncu capture of this same command (profiles/, tools/ncu_traffic.py);
+    # the algorithmic bytes per launch (operands + outputs once) are booked live by the C ABI next to the FLOPs
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic_r1.json")
+    if os.path.exists(tpath) and args.arch == "vit_base" and B == 64 and not args.no_aux:
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+    n_gemm = sum(c["launches"] for c in gemm) or 1
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN> (tcgen05.mma + TMA, all GEMMs of the forward)",
                 "achieved": g_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": g_tf / pk["tf_sustained"],
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["src"],
                 "share_of_step": sum(c["ms"] for c in gemm) / tot_ms,
-                "launches_per_step": sum(c["launches"] for c in gemm), "traffic": None}
+                "launches_per_step": sum(c["launches"] for c in gemm), "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, class average)",
+                "algorithmic_bytes_per_launch": sum(c["bytes"] for c in gemm) / n_gemm,
+                "algorithmic_flops_per_launch": sum(c["flops"] for c in gemm) / n_gemm}
     attn_info = {}
     for c in attn:
         attn_info[c["name"]] = {"ms_per_step": c["ms"], "tflops": tf([c]), "frac_of_tensor_peak": tf([c]) / pk["tf_sustained"],
