@@ -229,12 +229,12 @@ constexpr int EPI_SMEM_BYTES = 8 * EPI_WARP_WORDS * 4;
 
 template <int BN, int EK>
 __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, uint32_t tmem_acc, int row_base, int col_base,
-                                              int quarter, int half, int lane, float* sbuf) {
+                                              int quarter, int ew, int EW, int lane, float* sbuf) {   // warp ew of EW in this lane quarter
     const int r_lo = row_base + quarter * 32;
     if constexpr (EK == EK_HEAD) {   // column-major NCHW stores: lane == row is already the coalesced mapping
         const int row = r_lo + lane;
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        for (int c = ew * 32; c < BN; c += EW * 32) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
             tmem_ld_wait();
@@ -279,7 +279,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
             ps_b0 = m0 / gg; ps_i0 = ij / e.ps_g; ps_j0 = ij % e.ps_g;
         }
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        for (int c = ew * 32; c < BN; c += EW * 32) {
             const int n0 = col_base + c;
             if (n0 >= d.N) break;                     // N is a multiple of 32: chunks are all-valid or all-outside
             uint32_t r[32];
@@ -482,14 +482,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {  // ---------------- epilogue warps ----------------
         const int quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are this warp's
-        const int half = (warp - 2) >> 2;        // column half of the tile
+        const int ew = (warp - 2) >> 2;          // 32-column chunks ew, ew + 2, ... of the tile
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int m_blk = tile / n_blks, n_blk = tile % n_blks;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, m_blk * BM, n_blk * BN, quarter, half, lane,
+            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, m_blk * BM, n_blk * BN, quarter, ew, 2, lane,
                               reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES) + (warp - 2) * EPI_WARP_WORDS);
             tc_fence_before();
             __syncwarp();
@@ -526,15 +526,24 @@ template <int BN> struct TileCfg2 {
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024;
 };
+// Epilogue warps per TMEM lane quarter.  Two suffice when the epilogue is a handful of instructions per element; the GELU
+// epilogue of fc1 (9 instructions + 2 MUFU per element, 32768 elements per CTA tile) ran 9800 clk per tile on 8 warps --
+// latency-bound with two warps per scheduler -- against 7000 clk of MMA work, so it gets four per quarter (and, for the
+// shared-memory budget of their staging buffers, one pipeline stage less).
+template <int EK> struct EpiWarps { static constexpr int N = EK == EK_BF16_GELU ? 4 : 2; };
+template <int EK> __host__ __device__ constexpr int tc2_threads() { return (2 + 4 * EpiWarps<EK>::N) * 32; }
+template <int BN, int EK> __host__ __device__ constexpr int tc2_stages() { return TileCfg2<BN>::STAGES - (EpiWarps<EK>::N > 2 ? 1 : 0); }
+template <int BN, int EK> __host__ __device__ constexpr int tc2_smem() { return tc2_stages<BN, EK>() * TileCfg2<BN>::STAGE_BYTES + 4 * EpiWarps<EK>::N * EPI_WARP_WORDS * 4 + 1024; }
 
 template <int BN, int EK, int CL>   // CL = CTAs per cluster: 2 (one MMA pair) or 4 (two pairs sharing the B tile by TMA multicast)
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(tc2_threads<EK>(), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDims d,
                 const Epi e) {
     pdl_launch_dependents();
     using C = TileCfg2<BN>;
+    constexpr int STAGES = tc2_stages<BN, EK>();
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -549,13 +558,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < C::STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], PP);   // one multicast commit per pair that reads (and whose peers write) this stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 16);
+            mbar_init(&tempty_bar[s], 8 * EpiWarps<EK>::N);    // one elected lane per epilogue warp of both CTAs
         }
         fence_barrier_init();
     }
@@ -576,7 +585,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int pair = blockIdx.x / CL, npairs = gridDim.x / CL;      // cluster index / number of clusters
     constexpr uint16_t kAllMask = (uint16_t)((1u << CL) - 1);
     const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));
-    const int nst = d.stages > 0 && d.stages < C::STAGES ? d.stages : C::STAGES;
+    const int nst = d.stages > 0 && d.stages < STAGES ? d.stages : STAGES;
 
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------
@@ -647,15 +656,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else {  // ---------------- epilogue warps (both CTAs: own 128 rows, all BN columns) ----------------
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int ew = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair; tile < tiles; tile += npairs) {
             const int m_blk = tile / n_blks, n_blk = tile % n_blks;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, (m_blk * PP + pr) * 2 * BM + rank * BM, n_blk * BN, quarter, half,
-                              lane, reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES) + (warp - 2) * EPI_WARP_WORDS);
+            epilogue_tile<BN, EK>(e, d, tmem_base + acc * C::ACC_STRIDE, (m_blk * PP + pr) * 2 * BM + rank * BM, n_blk * BN, quarter, ew, EpiWarps<EK>::N,
+                              lane, reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES) + (warp - 2) * EPI_WARP_WORDS);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -767,8 +776,8 @@ template <int BN, int EK> static int attr1() {
     return 0;
 }
 template <int BN, int EK> static int attr2() {
-    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg2<BN>::SMEM_BYTES));
-    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg2<BN>::SMEM_BYTES));
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem<BN, EK>()));
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EK, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem<BN, EK>()));
     return 0;
 }
 template <int BN> static int attrs2_all() {
@@ -871,7 +880,7 @@ static int launch_tc2_cl(const GemmProblem& p, cudaStream_t stream) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 2;
-    cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = TileCfg2<BN>::SMEM_BYTES; cfg.stream = stream;
+    cfg.blockDim = dim3(tc2_threads<EK>()); cfg.dynamicSmemBytes = tc2_smem<BN, EK>(); cfg.stream = stream;
     static int max_clusters = 0;      // co-resident clusters of this instantiation (a persistent grid must not exceed it by much)
     if (max_clusters == 0) {
         cfg.gridDim = dim3(CL * (g_num_sms / CL));
