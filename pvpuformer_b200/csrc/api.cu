@@ -154,7 +154,7 @@ Plan make_plan(const vpu_context& h, int B) {
     p.add("P16", M * h.d.out_dims[2] * 2);
     p.add("D32a", (size_t)B * gh * gh * h.d32() * 2);
     p.add("P32", (size_t)B * gh * gh * h.d.out_dims[3] * 2);
-    p.add("gn_sums", (size_t)8 * B * 2 * sizeof(double));    // 8 GroupNorms x [B][sum, sum of squares]
+    p.add("gn_sums", (size_t)8 * B * 2 * sizeof(long long));    // 8 GroupNorms x [B][sum, sum of squares]
     // head
     const size_t res[4] = {g4, g2, g, gh};
     for (int i = 0; i < 4; ++i) {
@@ -203,8 +203,8 @@ struct Fwd {
 
     // GroupNorm fusion arguments of a neck GEMM (Epi::gn_*): statistics out, and / or the producer's GroupNorm folded in
     struct Gn {
-        double* out = nullptr;
-        const double* in = nullptr;
+        long long* out = nullptr;
+        const long long* in = nullptr;
         const float* wg = nullptr;
         int rows = 0;
         double in_count = 0;
@@ -245,7 +245,7 @@ struct Fwd {
         return timed("ln", 0, by, [&] { return layernorm_launch(a, h.C(), s); });
     }
     // GroupNorm apply (+GELU) with the statistics the producing GEMM accumulated: one read + one write of x
-    int gn(__nv_bfloat16* x, size_t per_sample, int Cc, const std::string& key, int gelu, const double* sums) {
+    int gn(__nv_bfloat16* x, size_t per_sample, int Cc, const std::string& key, int gelu, const long long* sums) {
         return timed("gn", 0, 4.0 * B * (double)per_sample, [&] {
             return groupnorm_apply_launch(x, B, per_sample, Cc, Wf(key + ".g"), Wf(key + ".b"), gelu, sums, s);
         });
@@ -299,7 +299,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
 
     // GroupNorm accumulators of the neck: cleared here so that no memset node sits between two kernels later on
     // (a non-kernel node would break the programmatic-dependent-launch chain, common.cuh)
-    VPU_CHECK_CUDA(cudaMemsetAsync(f.buf<double>("gn_sums"), 0, (size_t)8 * B * 2 * sizeof(double), s));
+    VPU_CHECK_CUDA(cudaMemsetAsync(f.buf<long long>("gn_sums"), 0, (size_t)8 * B * 2 * sizeof(long long), s));
     // ---- A1-A3, A7: fused image + coord-feature patch operand, one GEMM for both patch embeds ----
     CoordArgs ca;
     ca.image4 = image4; ca.points = pr.points; ca.extra_mask = pr.extra_mask; ca.n = pr.n; ca.H = img; ca.W = img;
@@ -440,7 +440,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     // GroupNorm(1, C) is fused into the GEMMs on both sides (Epi::gn_*): every GEMM accumulates the per-sample sum / sum of
     // squares of its fp32 outputs in its epilogue, the three GroupNorms that are not followed by GELU (d4.gn2, d8.gn1,
     // d32.gn1) are folded into the consuming 1x1 conv, and the other five need one apply (+GELU) pass and no statistics pass.
-    double* sums = f.buf<double>("gn_sums");     // zeroed at the top of the forward
+    long long* sums = f.buf<long long>("gn_sums");     // zeroed at the top of the forward
     auto S = [&](int i) { return sums + (size_t)i * B * 2; };
     typedef Fwd::Gn Gn;
     Gn gn;

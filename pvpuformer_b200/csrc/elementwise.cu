@@ -148,7 +148,7 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ partial, int chunk
 }
 // apply: every thread owns one channel octet (gamma / beta live in registers) and strides over pixels
 __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ x, size_t per_sample, int C,
-                                                       const float2* __restrict__ mean_rstd, const double* __restrict__ sums,
+                                                       const float2* __restrict__ mean_rstd, const long long* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int gelu) {
     pdl_launch_dependents();
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
     const int co = blockIdx.z * C8z + threadIdx.x % C8z, prow = threadIdx.x / C8z, rows_per_block = blockDim.x / C8z;
     float2 mr;
     if (sums) {      // (sum, sum of squares) accumulated by the producing GEMM's epilogue
-        const double inv_n = 1.0 / (double)per_sample, mean = sums[2 * b] * inv_n;
-        double var = sums[2 * b + 1] * inv_n - mean * mean;
+        const double inv_n = 1.0 / (double)per_sample, mean = (double)sums[2 * b] * (1.0 / (double)GN_SUM_SCALE) * inv_n;
+        double var = (double)sums[2 * b + 1] * (1.0 / (double)GN_SQ_SCALE) * inv_n - mean * mean;
         if (var < 0.0) var = 0.0;
         mr = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
     } else {
@@ -223,7 +223,7 @@ int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const fl
 
 // apply only: the statistics were accumulated by the GEMM epilogue that produced x (Epi::gn_out)
 int groupnorm_apply_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta, int gelu,
-                           const double* sums, cudaStream_t stream) {
+                           const long long* sums, cudaStream_t stream) {
     VPU_REQUIRE(per_sample % 8 == 0 && C % 8 == 0 && per_sample % C == 0, "groupnorm: sizes must be multiples of 8, C must divide the sample");
     const int C8 = C / 8;
     int zsplit = 1;

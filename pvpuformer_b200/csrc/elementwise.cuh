@@ -1,5 +1,6 @@
 #pragma once
 #include "common.cuh"
+#include "gemm.cuh"   // GN_SUM_SCALE / GN_SQ_SCALE
 
 namespace vpu {
 
@@ -24,7 +25,7 @@ constexpr int GN_MAX_CHUNKS = 1024;
 int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta,
                      int gelu, float2* partial, float2* mean_rstd, cudaStream_t stream);
 int groupnorm_apply_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const float* gamma, const float* beta, int gelu,
-                           const double* sums, cudaStream_t stream);
+                           const long long* sums, cudaStream_t stream);
 
 int qout_gate_launch(const float* q0, const float* q1, const float* q2, const float* q3, int B, int T, int C, float* qout,
                      __nv_bfloat16* qout_bf16, float* cg, cudaStream_t stream);

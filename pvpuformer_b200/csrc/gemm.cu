@@ -44,10 +44,10 @@ unsigned long long launch_count() { return g_launches.load(std::memory_order_rel
 // ------------------------------------------------------------------------------------------
 // Epilogue: CNT consecutive columns [n0, n0+CNT) of output row m.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gn_mean_rstd(const double* sums, int sample, float count, float& rstd, float& mean_rstd) {
+__device__ __forceinline__ void gn_mean_rstd(const long long* sums, int sample, float count, float& rstd, float& mean_rstd) {
     const double inv_n = 1.0 / (double)count;
-    const double mean = sums[2 * sample] * inv_n;
-    double var = sums[2 * sample + 1] * inv_n - mean * mean;
+    const double mean = (double)sums[2 * sample] * (1.0 / (double)GN_SUM_SCALE) * inv_n;
+    double var = (double)sums[2 * sample + 1] * (1.0 / (double)GN_SQ_SCALE) * inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
     const double r = 1.0 / sqrt(var + 1e-5);
     rstd = (float)r;
@@ -134,8 +134,8 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n0, float (&v
         float sum = 0.f, sq = 0.f;
 #pragma unroll
         for (int t = 0; t < CNT; ++t) { sum += v[t]; sq = fmaf(v[t], v[t], sq); }
-        atomicAdd(e.gn_out + 2 * (m / e.gn_rows), (double)sum);
-        atomicAdd(e.gn_out + 2 * (m / e.gn_rows) + 1, (double)sq);
+        atomicAdd(reinterpret_cast<unsigned long long*>(e.gn_out) + 2 * (m / e.gn_rows), (unsigned long long)__float2ll_rn(sum * GN_SUM_SCALE));
+        atomicAdd(reinterpret_cast<unsigned long long*>(e.gn_out) + 2 * (m / e.gn_rows) + 1, (unsigned long long)__float2ll_rn(sq * GN_SQ_SCALE));
     }
     if (e.act == ACT_GELU) {
 #pragma unroll
@@ -257,7 +257,8 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
         const bool stats = DYN ? (e.gn_out != nullptr) : (EK == EK_PS_ST || EK == EK_BF16_ST || EK == EK_GNIN_ST);
         const bool gnin = DYN ? (e.gn_in != nullptr) : (EK == EK_GNIN_ST);
         // a warp's 32 rows touch at most two samples (gn_rows >= 32): A = sample of the first row, B = the next one
-        float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f, rA = 1.f, mrA = 0.f, rB = 1.f, mrB = 0.f;
+        long long st_s0 = 0, st_q0 = 0, st_s1 = 0, st_q1 = 0;      // fixed point: see GN_SUM_SCALE
+        float rA = 1.f, mrA = 0.f, rB = 1.f, mrB = 0.f;
         int mB = 0x7fffffff, sA = 0;
         bool hasB = false;
         if ((stats || gnin) && r_lo < d.M) {
@@ -323,8 +324,9 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                     }
                     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     if (stats) {
-                        const float sm = (v.x + v.y) + (v.z + v.w);
-                        const float sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+                        // one row x four fixed columns: this fp32 partial does not depend on where the sample sits in the batch
+                        const long long sm = __float2ll_rn(((v.x + v.y) + (v.z + v.w)) * GN_SUM_SCALE);
+                        const long long sq = __float2ll_rn(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))) * GN_SQ_SCALE);
                         if (m >= mB) { st_s1 += sm; st_q1 += sq; } else { st_s0 += sm; st_q0 += sq; }
                     }
                     if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
@@ -357,14 +359,18 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
             __syncwarp();
         }
         if (stats) {
-            st_s0 = warp_sum(st_s0); st_q0 = warp_sum(st_q0);
-            st_s1 = warp_sum(st_s1); st_q1 = warp_sum(st_q1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                st_s0 += __shfl_xor_sync(0xffffffffu, st_s0, o); st_q0 += __shfl_xor_sync(0xffffffffu, st_q0, o);
+                st_s1 += __shfl_xor_sync(0xffffffffu, st_s1, o); st_q1 += __shfl_xor_sync(0xffffffffu, st_q1, o);
+            }
             if (lane == 0 && r_lo < d.M) {
-                atomicAdd(e.gn_out + 2 * sA, (double)st_s0);
-                atomicAdd(e.gn_out + 2 * sA + 1, (double)st_q0);
+                unsigned long long* acc = reinterpret_cast<unsigned long long*>(e.gn_out) + 2 * sA;
+                atomicAdd(acc, (unsigned long long)st_s0);
+                atomicAdd(acc + 1, (unsigned long long)st_q0);
                 if (hasB) {
-                    atomicAdd(e.gn_out + 2 * sA + 2, (double)st_s1);
-                    atomicAdd(e.gn_out + 2 * sA + 3, (double)st_q1);
+                    atomicAdd(acc + 2, (unsigned long long)st_s1);
+                    atomicAdd(acc + 3, (unsigned long long)st_q1);
                 }
             }
         }

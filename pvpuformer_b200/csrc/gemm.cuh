@@ -8,6 +8,9 @@ namespace vpu {
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum { EPI_PLAIN = 0, EPI_PIXEL_SHUFFLE = 1, EPI_HEAD_FINAL = 2 };
+// fixed-point scales of the GroupNorm accumulators: each fp32 partial (one row x four columns) is rounded to 2^-24 resp.
+// 2^-16 before it is added; int64 holds |sum| < 5e11 and a sum of squares < 1.4e14 per sample
+constexpr float GN_SUM_SCALE = 16777216.0f, GN_SQ_SCALE = 65536.0f;
 
 struct Epi {
     void* out = nullptr;            // [rows, ldo]; fp32 or bf16
@@ -33,12 +36,14 @@ struct Epi {
     float seg_bias = 0.f;
     int nq = 0;
     // GroupNorm(1, C) fusion for the neck (reference is_vpu_model.py:55-86; statistics over all values of one sample):
-    //   gn_out  [samples][2] doubles: += (sum, sum of squares) of this GEMM's fp32 outputs, per sample of gn_rows M-rows
+    //   gn_out  [samples][2] int64 fixed point (GN_SUM_SCALE / GN_SQ_SCALE): += (sum, sum of squares) of this GEMM's fp32
+    //           outputs, per sample of gn_rows M-rows.  Integer accumulation is associative, so the statistics -- and with
+    //           them the whole forward -- stay bit-identical whatever the batch size, tile assignment or atomic order
     //   gn_in   the same pair for the tensor the A operand holds un-normalised: the weights bound for this GEMM are
     //           W' = W diag(gamma) and bias = W beta + b, so GN folds into  out = rstd * acc - mean * rstd * gn_wg[n] + bias[n]
     //           with gn_wg[n] = sum_k W'[n, k]  (mean / rstd from gn_in over gn_in_count values, eps 1e-5)
-    double* gn_out = nullptr;
-    const double* gn_in = nullptr;
+    long long* gn_out = nullptr;
+    const long long* gn_in = nullptr;
     const float* gn_wg = nullptr;
     int gn_rows = 0;
     float gn_in_count = 0.f;
