@@ -219,6 +219,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs (its version banner included) go to STDOUT by default:
+                                                                  # keep the one JSON line alone there
         dist.init_process_group("nccl", device_id=dev)
     cfg = make_config(args.arch)
     model = build_model(args.arch, state_dict=synthetic_state_dict(cfg, 0), device=dev)

@@ -118,6 +118,17 @@ int vpu_gemm_pixel_shuffle(const void* A_bf16, const void* W_bf16, int M, int co
 int vpu_attention(const void* q, int ldq, int qoff, const void* k, int ldk, int koff, const void* v, int ldv, int voff,
                   void* o, int ldo, int Sq, int Sk, int heads, int head_dim, int nprob, float scale, int window,
                   int grid, void* stream);
+/* NoC evaluation protocol on the device (replaces isegm/inference/clicker.py:29-69 Clicker._get_next_click and
+ * isegm/inference/utils.py:80-87 get_iou for S click sessions at once).
+ *   gt          int8  [S,H,W]  1 object, 0 background, -1 ignore
+ *   pred        uint8 [S,H,W]  thresholded prediction (0/1)
+ *   not_clicked uint8 [S,H,W]  1 = not clicked yet; the chosen pixel is cleared
+ *   clicks      int32 [S,4]    (is_positive, row, col, squared distance of the click from the error-region border)
+ *   iou_counts  int64 [S,2]    (|pred & gt & keep|, |(pred | gt) & keep|): IoU = [0] / [1]
+ * Bit-exact with the reference's cv2.distanceTransform(DIST_L2, 0) clicker: integer squared distances throughout. */
+size_t vpu_noc_workspace_bytes(int S, int H, int W);
+int vpu_noc_next_clicks(const int8_t* gt, const uint8_t* pred, uint8_t* not_clicked, int S, int H, int W, int32_t* clicks,
+                        int64_t* iou_counts, void* workspace /* 256-byte aligned */, size_t workspace_bytes, void* stream);
 /* measurement only: CTA 0 of the following global-attention launches logs (event << 56 | clock64) per role into
  * dev_buf[4][cap] (uint64; roles: TMA thread, MMA thread, softmax warpgroup 0 / 1); NULL switches it off */
 int vpu_debug_attention_trace(void* dev_buf, int cap);

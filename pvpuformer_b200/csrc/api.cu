@@ -12,6 +12,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "noc.cuh"
 #include "prompt.cuh"
 
 namespace vpu {
@@ -803,6 +804,17 @@ int vpu_attention(const void* q, int ldq, int qoff, const void* k, int ldk, int 
         a.kmap.per_prob = Sk;
     }
     return attention_launch(a, head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t vpu_noc_workspace_bytes(int S, int H, int W) { return S > 0 && H > 0 && W > 0 ? noc_workspace_bytes(S, H, W) : 0; }
+
+int vpu_noc_next_clicks(const int8_t* gt, const uint8_t* pred, uint8_t* not_clicked, int S, int H, int W, int32_t* clicks,
+                        int64_t* iou_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    VPU_REQUIRE(gt && pred && not_clicked && clicks && iou_counts && workspace, "vpu_noc_next_clicks: null argument");
+    VPU_REQUIRE(workspace_bytes >= vpu_noc_workspace_bytes(S, H, W), "vpu_noc_next_clicks: workspace too small");
+    VPU_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vpu_noc_next_clicks: workspace must be 256-byte aligned");
+    return noc_next_clicks_launch(gt, pred, not_clicked, S, H, W, clicks, reinterpret_cast<long long*>(iou_counts), workspace,
+                                  reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vpu_debug_attention_trace(void* dev_buf, int cap) {

@@ -87,10 +87,16 @@ def _repack_points(points_nd, n):
 
 
 def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clicks=1, max_clicks=20, micro_batch=32,
-                      predictor_factory=vpu_eval_predictor, stats=None):
+                      predictor_factory=vpu_eval_predictor, stats=None, device_clicker=False):
     """samples: list of (image HWC, gt_mask HW).  Returns the list of per-sample IoU arrays, identical to running
     evaluate_sample on each (the forward is batch-independent), but with ONE network call per click per micro-batch.
-    `stats` (dict, optional) receives the number of network calls and click-forwards executed."""
+    `stats` (dict, optional) receives the number of network calls and click-forwards executed.
+
+    device_clicker=True keeps the ground truth, the thresholded predictions and the not-clicked maps of the micro-batch on
+    the device and gets the next clicks and the IoU counts of ALL its sessions from one call of the CUDA clicker
+    (csrc/noc.cu, bit-exact with the cv2 distance-transform clicker): per click the host reads back 16 + 16 bytes per
+    session instead of a full-resolution probability map and runs no distance transform.  All images of a micro-batch
+    must then have the same size."""
     results = [None] * len(samples)
     n_calls = n_fwd = 0
     with torch.no_grad():
@@ -104,6 +110,10 @@ def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clic
                     raise NotImplementedError("lock-step evaluation supports cascade_step <= 1")
                 p.set_input_image(image)
                 sess[i] = dict(pred=p, clicker=Clicker(gt_mask=gt), gt=gt, mask=np.zeros_like(gt), ious=[])
+            dc = _DeviceClickerBatch([sess[i]["gt"] for i in chunk], device) if device_clicker else None
+            slot = {i: k for k, i in enumerate(chunk)}
+            if dc is not None:
+                dc.step(None)                                   # first clicks: prediction = all background
             active = list(chunk)
             for click_indx in range(max_clicks):
                 if not active:
@@ -111,7 +121,10 @@ def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clic
                 prepared = []
                 for i in active:
                     s = sess[i]
-                    s["clicker"].make_next_click(s["mask"])
+                    if dc is None:
+                        s["clicker"].make_next_click(s["mask"])
+                    else:
+                        s["clicker"].add_click(dc.click(slot[i]))
                     image_nd, points_nd, _ = s["pred"].prepare_inputs(s["clicker"], None, s["gt"], 0)
                     prepared.append((image_nd, points_nd))
                 n = max(p.shape[1] // 2 for _, p in prepared)
@@ -121,15 +134,23 @@ def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clic
                 n_calls += 1
                 n_fwd += images.shape[0]
                 still, row = [], 0
+                preds = {}
                 for i, (image_nd, _) in zip(active, prepared):
                     s = sess[i]
                     r = image_nd.shape[0]
                     pred = s["pred"].finish_prediction(logits[row:row + r], image_nd.shape[2:])
                     row += r
                     s["pred"].prev_prediction = pred
-                    probs = pred.cpu().numpy()[0, 0]
-                    s["mask"] = probs > pred_thr
-                    iou = get_iou(s["gt"], s["mask"])
+                    if dc is None:
+                        probs = pred.cpu().numpy()[0, 0]
+                        s["mask"] = probs > pred_thr
+                    else:
+                        preds[slot[i]] = pred[0, 0] > pred_thr
+                if dc is not None:
+                    dc.step(preds)                              # IoU of this click + the next click, all sessions at once
+                for i in active:
+                    s = sess[i]
+                    iou = dc.iou(slot[i]) if dc is not None else get_iou(s["gt"], s["mask"])
                     s["ious"].append(iou)
                     if not (iou >= max_iou_thr and click_indx + 1 >= min_clicks):
                         still.append(i)
@@ -140,6 +161,41 @@ def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clic
         stats["network_calls"] = stats.get("network_calls", 0) + n_calls
         stats["click_forwards"] = stats.get("click_forwards", 0) + n_fwd
     return results
+
+
+class _DeviceClickerBatch:
+    """Ground truth / prediction / not-clicked maps of one micro-batch on the device + one clicker call per click."""
+
+    def __init__(self, gts, device):
+        from .. import ops
+        self.ops = ops
+        shapes = {g.shape for g in gts}
+        if len(shapes) != 1:
+            raise ValueError("device_clicker needs equally sized images inside a micro-batch, got %s" % sorted(shapes))
+        if gts[0].shape[0] * gts[0].shape[1] < 20000:
+            raise ValueError("device_clicker is bit-exact with the cv2 clicker only for masks of >= 2e4 pixels (csrc/noc.cu); "
+                             "use device_clicker=False for %s" % (gts[0].shape,))
+        self.gt = torch.from_numpy(np.stack([np.asarray(g).astype(np.int8) for g in gts])).to(device)
+        self.pred = torch.zeros(self.gt.shape, dtype=torch.uint8, device=device)
+        self.not_clicked = torch.ones(self.gt.shape, dtype=torch.uint8, device=device)
+        self.workspace = None
+        self.clicks = self.counts = None
+
+    def step(self, preds):
+        """preds: {slot: bool [H,W] device tensor} of the sessions that ran this click (others keep their last mask)."""
+        if preds:
+            for k, p in preds.items():
+                self.pred[k] = p
+        clicks, counts = self.ops.noc_next_clicks(self.gt, self.pred, self.not_clicked)
+        self.clicks, self.counts = clicks.cpu().numpy(), counts.cpu().numpy()       # 32 bytes per session
+
+    def click(self, k):
+        from .clicker import Click
+        c = self.clicks[k]
+        return Click(is_positive=bool(c[0]), coords=(int(c[1]), int(c[2])))
+
+    def iou(self, k):
+        return self.counts[k, 0] / self.counts[k, 1]           # numpy int64 / int64 -> float64, as get_iou
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -74,3 +74,21 @@ def upsample_align_corners(x, H, W):
     L.check(L.load().vpu_upsample_align_corners(L.ptr(x), L.ptr(out), x.shape[-2], x.shape[-1], H, W, planes,
                                                 L.current_stream()))
     return out
+
+
+def noc_next_clicks(gt, pred, not_clicked, workspace=None):
+    """Device-side oracle clicker + IoU counts (csrc/noc.cu; reference inference/clicker.py:29-69, inference/utils.py:80-87).
+    gt int8 [S,H,W] (1 object / 0 background / -1 ignore), pred uint8 [S,H,W], not_clicked uint8 [S,H,W] (updated in place)
+    -> (clicks int32 [S,4] = is_positive,row,col,d2 ; counts int64 [S,2] = intersection, union), both on the device."""
+    S, H, W = gt.shape
+    assert gt.dtype == torch.int8 and pred.dtype == torch.uint8 and not_clicked.dtype == torch.uint8
+    assert pred.shape == gt.shape and not_clicked.shape == gt.shape and gt.is_contiguous() and pred.is_contiguous() and not_clicked.is_contiguous()
+    lib = L.load()
+    need = lib.vpu_noc_workspace_bytes(S, H, W)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=gt.device)
+    clicks = torch.empty(S, 4, dtype=torch.int32, device=gt.device)
+    counts = torch.empty(S, 2, dtype=torch.int64, device=gt.device)
+    L.check(lib.vpu_noc_next_clicks(L.ptr(gt), L.ptr(pred), L.ptr(not_clicked), S, H, W, L.ptr(clicks), L.ptr(counts), L.ptr(workspace),
+                                    workspace.numel(), L.current_stream()))
+    return clicks, counts

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pvpuformer_b200.config import make_config  # noqa: E402
 from pvpuformer_b200.inference import compute_noc_metric  # noqa: E402
 from pvpuformer_b200.inference.datasets import SyntheticEllipseDataset  # noqa: E402
-from pvpuformer_b200.inference.evaluation import evaluate_sharded  # noqa: E402
+from pvpuformer_b200.inference.evaluation import evaluate_lockstep, evaluate_sharded  # noqa: E402
 from pvpuformer_b200.model import build_model  # noqa: E402
 from pvpuformer_b200.weights import synthetic_state_dict  # noqa: E402
 
@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--images", type=int, default=64)
     ap.add_argument("--clicks", type=int, default=20)
     ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--host-clicker", action="store_true", help="cv2 distance-transform clicker + IoU on the host (default: csrc/noc.cu)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -38,19 +39,24 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs (its version banner included) go to STDOUT by default:
+                                                                  # keep the one JSON line alone there
         dist.init_process_group("nccl", device_id=dev)
     cfg = make_config(args.arch)
     model = build_model(args.arch, state_dict=synthetic_state_dict(cfg, 0), device=dev)
     model.want_aux = False                        # NoBRS reads only ['instances'] (reference predictors/base.py:177)
     ds = SyntheticEllipseDataset(args.images)
     # warm-up: one small shard-independent pass (weights packed, workspaces allocated)
-    evaluate_sharded(SyntheticEllipseDataset(2, seed0=10_000), model, dev, 0, 1, 1.01, max_clicks=2, micro_batch=2)
+    wds = SyntheticEllipseDataset(2, seed0=10_000)
+    evaluate_lockstep([(wds.get_sample(i).image, wds.get_sample(i).gt_mask(1)) for i in range(2)], model, dev, 1.01, max_clicks=2,
+                      micro_batch=2)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     table, local_s, stats = evaluate_sharded(ds, model, dev, rank, world, 1.01, max_clicks=args.clicks,
-                                             micro_batch=args.micro_batch, gather_device=dev if world > 1 else None)
+                                             micro_batch=args.micro_batch, gather_device=dev if world > 1 else None,
+                                             device_clicker=not args.host_clicker)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -63,7 +69,7 @@ def main():
         noc, _, over = compute_noc_metric([r[np.isfinite(r)] for r in table], [0.8, 0.85, 0.9], max_clicks=args.clicks)
         fwd = 2 * args.images * args.clicks
         print(json.dumps({"metric": "click-forwards/sec (NoC loop, host work included)", "value": fwd / total_s, "n_gpus": world,
-                          "arch": args.arch, "images": args.images, "clicks": args.clicks, "micro_batch": args.micro_batch,
+                          "arch": args.arch, "images": args.images, "clicks": args.clicks, "micro_batch": args.micro_batch, "clicker": "host" if args.host_clicker else "device",
                           "seconds": total_s, "rank0_loop_seconds": local_s, "rank0_network_calls": stats["network_calls"],
                           "noc@80/85/90": [float(x) for x in noc], "iou_table_shape": list(table.shape)}), flush=True)
     if world > 1:
