@@ -41,3 +41,21 @@ def first_clicks_in_masks(masks, seed, n=2):
         i = rs.randint(len(ys))
         pts[b, 0] = torch.tensor([float(ys[i]), float(xs[i]), 0.])
     return pts
+
+
+def train12_inputs():
+    """ViT-B training shape -- batch 12, points [12, 48, 3] (n = 24 rows per half) with 1-3 valid
+    clicks per half, ellipse ground truth; -> (image4, points, gt [12,1,448,448] float)."""
+    B, n = 12, 24
+    masks = ellipse_masks(B, seed=9)
+    rs = np.random.RandomState(10)
+    pts = torch.full((B, 2 * n, 3), -1.0, dtype=torch.float32)
+    for b in range(B):
+        order = 0
+        for half, inside in ((0, True), (1, False)):
+            ys, xs = np.nonzero(masks[b] > 0.5 if inside else masks[b] < 0.5)
+            for j in range(rs.randint(1, 4)):
+                i = rs.randint(len(ys))
+                pts[b, half * n + j] = torch.tensor([float(ys[i]), float(xs[i]), float(order)])
+                order += 1
+    return images(B, seed=8), pts, torch.from_numpy(masks)[:, None]

@@ -74,6 +74,22 @@ def pack(out, taps):
     return d
 
 
+def train12(model):
+    from isegm.model.losses import DiceLoss, NormalizedFocalLossSigmoid, SigmoidBinaryCrossEntropyLoss
+    from oracle import losses as ol
+    image4, pts, gt = cases.train12_inputs()
+    out, taps = run_reference(model, image4, pts)
+    nfl = NormalizedFocalLossSigmoid(alpha=0.5, gamma=2, penalty_loss=False)(out["instances"], gt)
+    dice = DiceLoss(use_sigmoid=True, activate=True, naive_dice=True, loss_weight=1.0)(out["instances"], gt)
+    bce = SigmoidBinaryCrossEntropyLoss(from_sigmoid=True)(out["instances_aux"], ol.ed_mask_label(gt))
+    keep = {"ppue_support_packed": np.packbits(taps["ppue"].numpy() != 0),          # all 48 rows in use (n = 24 per half)
+            "seg_lowres_s4": taps["seg_lowres"][:, :, ::4, ::4].numpy(),
+            "instances_row100": out["instances"][:, 0, 100, :].numpy(),
+            "aux_s16_sel": out["instances_aux"][:, [0, 24], ::16, ::16].numpy()}
+    np.savez_compressed(os.path.join(OUT, "vit_base_train12.npz"), loss_nfl=nfl.numpy(), loss_dice=dice.numpy(),
+                        loss_bce_aux=bce.numpy(), **keep)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     rh.import_reference()
@@ -108,6 +124,9 @@ def main():
     pts = cases.random_clicks(3, seed=6)
     out, taps = run_reference(model, image4, pts)
     np.savez_compressed(os.path.join(OUT, "vit_base_manyclicks.npz"), **pack(out, taps))
+
+    # case 5: training shape, B=12, points [12,48,3]; the reference's own loss classes on its outputs
+    train12(model)
     del model
 
     for arch in ("vit_large", "vit_huge"):

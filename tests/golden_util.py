@@ -18,6 +18,9 @@ def case_inputs(name):
     """-> (image4, points, prompts, as_prompt_type) exactly as oracle/make_golden.py built them."""
     if name.endswith("_clicks"):
         return cases.images(2, seed=1), cases.CLICKS_A.clone(), None, 0
+    if name.endswith("_train12"):
+        image4, pts, _ = cases.train12_inputs()
+        return image4, pts, None, 0
     if name.endswith("_manyclicks"):
         return cases.images(3, seed=5), cases.random_clicks(3, seed=6), None, 0
     g = load(name)

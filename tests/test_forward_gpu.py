@@ -101,6 +101,27 @@ def test_forward_vs_reference_golden_large_huge(arch):
     assert np.abs(seg_low - g["seg_lowres"]).max() <= LOGIT_TOL
 
 
+def test_training_shape_forward_and_losses_vs_reference_golden():
+    """SURVEY 8d config 5 (forward-path parity of the training shape): batch 12, points [12,48,3] (all 48 PPuE rows in
+    use), outputs and the three loss terms of the reference's training config -- NFL + Dice on `instances`, BCE on the
+    P2CL probabilities -- against what the unmodified reference produced (fixture made by oracle/make_golden.py)."""
+    from oracle import losses as ol
+    m, _ = _model("vit_base")
+    image4, pts, gt = cases.train12_inputs()
+    g = gu.load("vit_base_train12")
+    out = m(image4.cuda(), pts.cuda())
+    rows = m.ppue(pts.cuda()).cpu().numpy()
+    assert np.array_equal(np.packbits(rows != 0), g["ppue_support_packed"])
+    inst, aux = out["instances"].cpu(), out["instances_aux"].cpu()
+    assert np.abs(inst[:, 0, 100, :].numpy() - g["instances_row100"]).max() <= LOGIT_TOL
+    assert np.abs(aux[:, [0, 24], ::16, ::16].numpy() - g["aux_s16_sel"]).max() <= AUX_TOL
+    ls = ol.training_losses({"instances": inst, "instances_aux": aux}, gt)
+    # bf16 forward vs fp32 reference: loss terms are means over 2e5 .. 9.6e6 values, so they agree far inside the per-pixel gate
+    assert np.abs(ls["nfl"].numpy() - g["loss_nfl"]).max() <= 2e-3
+    assert abs(float(ls["dice"]) - float(g["loss_dice"])) <= 2e-3
+    assert np.abs(ls["bce_aux"].numpy() - g["loss_bce_aux"]).max() <= 2e-3
+
+
 def test_forward_vs_oracle_stress_weights_relative_error():
     """xavier-everywhere weights give ~8x larger logits (std ~0.2): the absolute gate no longer has the
     10x headroom it has at the reference's init scale, so the error is gated relative to the logit std."""

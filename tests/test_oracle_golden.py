@@ -84,3 +84,21 @@ def test_disk_maps_edges():
     assert d[0, 0].sum() == 26            # quarter disk incl. axes at a corner
     empty = vo.disk_maps(torch.full((2, 2, 3), -1.0), 448, 448)
     assert empty.sum() == 0
+
+
+def test_oracle_training_shape_case_losses_match_reference_golden():
+    """batch 12, points [12,48,3]; the oracle forward + the restated losses reproduce the loss values
+    the reference's own loss classes gave on the reference's outputs."""
+    from oracle import cases, losses as ol
+    cfg = make_config("vit_base")
+    image4, pts, gt = cases.train12_inputs()
+    g = gu.load("vit_base_train12")
+    taps = {}
+    with torch.no_grad():
+        out = vo.forward(_sd("vit_base"), cfg, image4, pts, taps=taps)
+        ls = ol.training_losses(out, gt)
+    assert np.array_equal(np.packbits(taps["ppue"].numpy() != 0), g["ppue_support_packed"])
+    assert np.abs(out["instances"][:, 0, 100, :].numpy() - g["instances_row100"]).max() < 1e-4
+    assert np.abs(ls["nfl"].numpy() - g["loss_nfl"]).max() < 1e-5
+    assert abs(float(ls["dice"]) - float(g["loss_dice"])) < 1e-5
+    assert np.abs(ls["bce_aux"].numpy() - g["loss_bce_aux"]).max() < 1e-5

@@ -53,3 +53,23 @@ def test_ppue_fuzz_vs_reference():
         assert torch.equal(a, b)
         disks_ref = m.dist_maps(torch.zeros(3, 3, 448, 448), pts.clone())
         assert torch.equal(disks_ref, vo.disk_maps(pts, 448, 448))
+
+
+def test_training_losses_bitexact_vs_reference_classes():
+    """oracle/losses.py against the reference's own loss modules (configuration of vpu_base448_cocolvis.py:72-80) on random
+    logits / probabilities with an ignore region."""
+    rh.import_reference()
+    from isegm.model.losses import DiceLoss, NormalizedFocalLossSigmoid, SigmoidBinaryCrossEntropyLoss
+    from oracle import losses as ol
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(3, 1, 64, 64, generator=g) * 2
+    gt = (torch.rand(3, 1, 64, 64, generator=g) > 0.6).float()
+    gt_ign = gt.clone()
+    gt_ign[:, :, :5] = -1
+    aux = torch.rand(3, 48, 64, 64, generator=g)
+    assert torch.equal(NormalizedFocalLossSigmoid(alpha=0.5, gamma=2, penalty_loss=False)(logits, gt_ign),
+                       ol.normalized_focal_loss_sigmoid(logits, gt_ign))
+    assert torch.equal(DiceLoss(use_sigmoid=True, activate=True, naive_dice=True, loss_weight=1.0)(logits, gt),
+                       ol.dice_loss_sigmoid_naive(logits, gt))
+    lab = ol.ed_mask_label(gt)
+    assert torch.equal(SigmoidBinaryCrossEntropyLoss(from_sigmoid=True)(aux, lab), ol.sigmoid_bce_from_sigmoid(aux, lab))
