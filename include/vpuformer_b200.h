@@ -129,6 +129,38 @@ int vpu_attention(const void* q, int ldq, int qoff, const void* k, int ldk, int 
 size_t vpu_noc_workspace_bytes(int S, int H, int W);
 int vpu_noc_next_clicks(const int8_t* gt, const uint8_t* pred, uint8_t* not_clicked, int S, int H, int W, int32_t* clicks,
                         int64_t* iou_counts, void* workspace /* 256-byte aligned */, size_t workspace_bytes, void* stream);
+/* Device-resident NoBRS click sessions: the predictor transforms either side of vpu_forward for S sessions at once
+ * (SURVEY.md 8(f) rank 2).  Replaces, per click and per session, BasePredictor's input assembly and get_points_nd
+ * (isegm/inference/predictors/base.py:106-151,195-213), ZoomIn.transform / _transform_clicks / inv_transform
+ * (transforms/zoom_in.py:30-112), AddHorizontalFlip (transforms/flip.py:9-28) and SigmoidForPred (transforms/base.py:29-38)
+ * in the configuration of scripts/evaluate_vpumodel.py:187-192 (skip_clicks = -1, fixed square target size, flip TTA).
+ * All pointers are device memory owned by the caller; the state persists between clicks.  Initial state: prev_probs = 0,
+ * pred = 0, nclicks = 0, roi = -1, fgbox = {INT32_MAX, -1, INT32_MAX, -1, -1}. */
+typedef struct vpu_session_state {
+    int32_t S, H, W;              /* sessions, full image size (equal for all sessions of the batch) */
+    int32_t T;                    /* network input side = ZoomIn target_size (448) */
+    int32_t max_clicks;           /* rows of the click table per session (<= 64) */
+    int32_t n_half;               /* points per half written for the network (>= max_clicks, <= num_max_points) */
+    const float* images;          /* [S,3,H,W] fp32 in [0,1] */
+    float* prev_probs;            /* [S,H,W] last full-size probability map (prev_prediction / ZoomIn._prev_probs) */
+    uint8_t* pred;                /* [S,H,W] prev_probs > pred_thr: the `pred` operand of vpu_noc_next_clicks */
+    int32_t* clicks;              /* [S,max_clicks,3] (is_positive, row, col) in click order */
+    int32_t* nclicks;             /* [S] */
+    int32_t* roi;                 /* [S,4] zoom-in region rmin,rmax,cmin,cmax (inclusive); roi[0] < 0: none yet */
+    int32_t* fgbox;               /* [S,5] bbox of prev_probs > zoom_thr and a state word (-1 no prediction yet, 0 empty, 1 set) */
+    float pred_thr;               /* 0.49 (evaluate_vpumodel.py: --thresh) */
+    float zoom_thr;               /* 0.5 (ZoomIn.prob_thresh) */
+    double expansion_ratio;       /* 1.4 */
+    double recompute_thresh_iou;  /* 0.5 */
+    int32_t min_crop_size;        /* 200; < 0 = None */
+} vpu_session_state;
+/* Before the forward: for each a < A, session s = active[a] appends new_clicks[s] = (is_positive,row,col,.) (the row
+ * vpu_noc_next_clicks wrote; NULL = no new click), updates its zoom-in region, and writes network rows a (crop) and A + a
+ * (mirrored crop): net_image [2A,4,T,T] fp32 (RGB + previous probabilities), net_points [2A, 2*n_half, 3] float64. */
+int vpu_session_prepare(const vpu_session_state* st, const int32_t* active, int A, const int32_t* new_clicks /* [S,4] or NULL */,
+                        float* net_image, double* net_points, void* stream);
+/* After the forward: logits [2A,1,T,T] (rows a and A + a) -> prev_probs, pred and fgbox of session active[a]. */
+int vpu_session_finish(const vpu_session_state* st, const int32_t* active, int A, const float* logits, void* stream);
 /* measurement only: CTA 0 of the following global-attention launches logs (event << 56 | clock64) per role into
  * dev_buf[4][cap] (uint64; roles: TMA thread, MMA thread, softmax warpgroup 0 / 1); NULL switches it off */
 int vpu_debug_attention_trace(void* dev_buf, int cap);

@@ -14,6 +14,7 @@
 #include "gemm.cuh"
 #include "noc.cuh"
 #include "prompt.cuh"
+#include "session.cuh"
 
 namespace vpu {
 const char* last_error();
@@ -815,6 +816,26 @@ int vpu_noc_next_clicks(const int8_t* gt, const uint8_t* pred, uint8_t* not_clic
     VPU_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vpu_noc_next_clicks: workspace must be 256-byte aligned");
     return noc_next_clicks_launch(gt, pred, not_clicked, S, H, W, clicks, reinterpret_cast<long long*>(iou_counts), workspace,
                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+static SessionState to_session(const vpu_session_state* st) {
+    SessionState s;
+    s.S = st->S; s.H = st->H; s.W = st->W; s.T = st->T; s.max_clicks = st->max_clicks; s.n_half = st->n_half;
+    s.images = st->images; s.prev_probs = st->prev_probs; s.pred = st->pred; s.clicks = st->clicks; s.nclicks = st->nclicks;
+    s.roi = st->roi; s.fgbox = st->fgbox; s.pred_thr = st->pred_thr; s.zoom_thr = st->zoom_thr;
+    s.expansion_ratio = st->expansion_ratio; s.recompute_thresh_iou = st->recompute_thresh_iou; s.min_crop_size = st->min_crop_size;
+    return s;
+}
+
+int vpu_session_prepare(const vpu_session_state* st, const int32_t* active, int A, const int32_t* new_clicks, float* net_image,
+                        double* net_points, void* stream) {
+    VPU_REQUIRE(st, "vpu_session_prepare: null state");
+    return session_prepare_launch(to_session(st), active, A, new_clicks, net_image, net_points, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_session_finish(const vpu_session_state* st, const int32_t* active, int A, const float* logits, void* stream) {
+    VPU_REQUIRE(st, "vpu_session_finish: null state");
+    return session_finish_launch(to_session(st), active, A, logits, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vpu_debug_attention_trace(void* dev_buf, int cap) {

@@ -87,7 +87,7 @@ def _repack_points(points_nd, n):
 
 
 def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clicks=1, max_clicks=20, micro_batch=32,
-                      predictor_factory=vpu_eval_predictor, stats=None, device_clicker=False):
+                      predictor_factory=vpu_eval_predictor, stats=None, device_clicker=False, device_session=False):
     """samples: list of (image HWC, gt_mask HW).  Returns the list of per-sample IoU arrays, identical to running
     evaluate_sample on each (the forward is batch-independent), but with ONE network call per click per micro-batch.
     `stats` (dict, optional) receives the number of network calls and click-forwards executed.
@@ -96,7 +96,17 @@ def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clic
     the device and gets the next clicks and the IoU counts of ALL its sessions from one call of the CUDA clicker
     (csrc/noc.cu, bit-exact with the cv2 distance-transform clicker): per click the host reads back 16 + 16 bytes per
     session instead of a full-resolution probability map and runs no distance transform.  All images of a micro-batch
-    must then have the same size."""
+    must then have the same size.
+
+    device_session=True additionally keeps the images, the previous probabilities, the click lists and the zoom-in regions
+    on the device and runs the predictor transforms either side of the network as CUDA kernels (csrc/session.cu,
+    inference/device_session.py): no per-session host work and no read-back inside the click loop."""
+    if device_session:
+        if predictor_factory is not vpu_eval_predictor:
+            raise ValueError("device sessions implement the vpu_eval_predictor configuration only")
+        from .device_session import evaluate_device_sessions
+        return evaluate_device_sessions(samples, net, device, max_iou_thr, pred_thr=pred_thr, min_clicks=min_clicks,
+                                        max_clicks=max_clicks, micro_batch=micro_batch, stats=stats)
     results = [None] * len(samples)
     n_calls = n_fwd = 0
     with torch.no_grad():
@@ -192,7 +202,9 @@ class _DeviceClickerBatch:
     def click(self, k):
         from .clicker import Click
         c = self.clicks[k]
-        return Click(is_positive=bool(c[0]), coords=(int(c[1]), int(c[2])))
+        # numpy int64 coordinates, as np.where gives them to the reference's clicker (clicker.py:55-69): the ZoomIn-rescaled
+        # coordinates then are numpy float64 scalars and get_points_nd builds a float64 tensor, not a float32 one
+        return Click(is_positive=bool(c[0]), coords=(np.int64(c[1]), np.int64(c[2])))
 
     def iou(self, k):
         return self.counts[k, 0] / self.counts[k, 1]           # numpy int64 / int64 -> float64, as get_iou

@@ -31,6 +31,13 @@ class VpuPrompts(ctypes.Structure):
                 ("extra_mask", c_void_p)]
 
 
+class VpuSessionState(ctypes.Structure):
+    _fields_ = [("S", c_int32), ("H", c_int32), ("W", c_int32), ("T", c_int32), ("max_clicks", c_int32), ("n_half", c_int32),
+                ("images", c_void_p), ("prev_probs", c_void_p), ("pred", c_void_p), ("clicks", c_void_p), ("nclicks", c_void_p),
+                ("roi", c_void_p), ("fgbox", c_void_p), ("pred_thr", c_float), ("zoom_thr", c_float),
+                ("expansion_ratio", c_double), ("recompute_thresh_iou", c_double), ("min_crop_size", c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/vpuformer_b200.h declares
 SIGNATURES = {
     "vpu_last_error": (c_char_p, []),
@@ -56,6 +63,8 @@ SIGNATURES = {
                               c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "vpu_noc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vpu_noc_next_clicks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vpu_session_prepare": (c_int, [POINTER(VpuSessionState), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vpu_session_finish": (c_int, [POINTER(VpuSessionState), c_void_p, c_int, c_void_p, c_void_p]),
     "vpu_debug_attention_trace": (c_int, [c_void_p, c_int]),
     "vpu_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),

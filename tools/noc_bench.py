@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--clicks", type=int, default=20)
     ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--host-clicker", action="store_true", help="cv2 distance-transform clicker + IoU on the host (default: csrc/noc.cu)")
+    ap.add_argument("--host-transforms", action="store_true",
+                    help="per-session Python predictors (ZoomIn / flip / sigmoid as torch ops) instead of the device sessions of csrc/session.cu")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -56,7 +58,8 @@ def main():
     t0 = time.perf_counter()
     table, local_s, stats = evaluate_sharded(ds, model, dev, rank, world, 1.01, max_clicks=args.clicks,
                                              micro_batch=args.micro_batch, gather_device=dev if world > 1 else None,
-                                             device_clicker=not args.host_clicker)
+                                             device_clicker=not args.host_clicker,
+                                             device_session=not (args.host_clicker or args.host_transforms))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -70,6 +73,7 @@ def main():
         fwd = 2 * args.images * args.clicks
         print(json.dumps({"metric": "click-forwards/sec (NoC loop, host work included)", "value": fwd / total_s, "n_gpus": world,
                           "arch": args.arch, "images": args.images, "clicks": args.clicks, "micro_batch": args.micro_batch, "clicker": "host" if args.host_clicker else "device",
+                          "transforms": "host" if (args.host_clicker or args.host_transforms) else "device",
                           "seconds": total_s, "rank0_loop_seconds": local_s, "rank0_network_calls": stats["network_calls"],
                           "noc@80/85/90": [float(x) for x in noc], "iou_table_shape": list(table.shape)}), flush=True)
     if world > 1:
