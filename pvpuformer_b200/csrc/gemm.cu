@@ -213,7 +213,8 @@ enum EpiKind {
     // algebraically (no apply pass for the GroupNorms that are not followed by GELU)
     EK_PS_ST = 8,      // EK_PS + statistics
     EK_BF16_ST = 9,    // EK_BF16 + statistics
-    EK_GNIN_ST = 10    // out bf16 = rstd*acc - mean*rstd*wg + bias, + statistics
+    EK_GNIN_ST = 10,   // out bf16 = rstd*acc - mean*rstd*wg + bias, + statistics
+    EK_F32_RESBF = 11  // out fp32 = acc + bias + residual bf16       (DMA image<-token out_proj on the bf16 keys)
 };
 
 // measurement-only ablation (VPU_GEMM_ABLATE) is compiled in with -DVPU_GEMM_DEBUG: the check sat in the MMA issue loop
@@ -248,9 +249,9 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
         }
     } else {
         constexpr bool DYN = EK == EK_GENERIC;
-        const bool has_res = DYN ? (e.res != nullptr) : (EK == EK_F32_RES);
-        const bool res_bf16 = DYN ? (e.res_bf16 != 0) : false;
-        const bool out_bf16 = DYN ? (e.out_bf16 != 0) : (EK != EK_F32_RES);
+        const bool has_res = DYN ? (e.res != nullptr) : (EK == EK_F32_RES || EK == EK_F32_RESBF);
+        const bool res_bf16 = DYN ? (e.res_bf16 != 0) : (EK == EK_F32_RESBF);
+        const bool out_bf16 = DYN ? (e.out_bf16 != 0) : (EK != EK_F32_RES && EK != EK_F32_RESBF);
         const int act = DYN ? e.act : (EK == EK_BF16_GELU ? ACT_GELU : (EK == EK_BF16_RELU ? ACT_RELU : ACT_NONE));
         const bool has_tab = DYN ? (e.bias2d != nullptr) : (EK == EK_BF16_TAB);
         const bool pshuf = DYN ? (e.mode == EPI_PIXEL_SHUFFLE) : (EK == EK_PS || EK == EK_PS_ST);
@@ -307,6 +308,15 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                     }
                 }
             }
+            float4 tabv[8];
+            if (has_tab) {                           // like the residual: all eight rows in flight before the accumulator is needed
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    int trow = trow0 + 4 * it;                           // table rows >= 32 on this path: at most one wrap
+                    while (trow >= e.bias2d_rows) trow -= e.bias2d_rows;
+                    tabv[it] = __ldg(reinterpret_cast<const float4*>(e.bias2d + (size_t)trow * d.N + n));
+                }
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -330,12 +340,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                         if (m >= mB) { st_s1 += sm; st_q1 += sq; } else { st_s0 += sm; st_q0 += sq; }
                     }
                     if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
-                    if (has_tab) {
-                        int trow = trow0 + 4 * it;                       // table rows >= 32 on this path: at most one wrap
-                        while (trow >= e.bias2d_rows) trow -= e.bias2d_rows;
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias2d + (size_t)trow * d.N + n));
-                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                    }
+                    if (has_tab) { v.x += tabv[it].x; v.y += tabv[it].y; v.z += tabv[it].z; v.w += tabv[it].w; }
                     if (act == ACT_GELU) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
                     else if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     size_t orow = (size_t)m;
@@ -536,7 +541,9 @@ template <int BN> struct TileCfg2 {
 // epilogue of fc1 (9 instructions + 2 MUFU per element, 32768 elements per CTA tile) ran 9800 clk per tile on 8 warps --
 // latency-bound with two warps per scheduler -- against 7000 clk of MMA work, so it gets four per quarter (and, for the
 // shared-memory budget of their staging buffers, one pipeline stage less).
-template <int EK> struct EpiWarps { static constexpr int N = EK == EK_BF16_GELU ? 4 : 2; };
+// The same holds for the K = 384 out_proj of the DMA image<-token attention (6 k-blocks of MMA per 128 KB of fp32 output per CTA:
+// 94 -> 60 us with four).  Four warps per quarter on the neck / table epilogues measured no gain on the whole step.
+template <int EK> struct EpiWarps { static constexpr int N = (EK == EK_BF16_GELU || EK == EK_F32_RESBF) ? 4 : 2; };
 template <int EK> __host__ __device__ constexpr int tc2_threads() { return (2 + 4 * EpiWarps<EK>::N) * 32; }
 template <int BN, int EK> __host__ __device__ constexpr int tc2_stages() { return TileCfg2<BN>::STAGES - (EpiWarps<EK>::N > 2 ? 1 : 0); }
 template <int BN, int EK> __host__ __device__ constexpr int tc2_smem() { return tc2_stages<BN, EK>() * TileCfg2<BN>::STAGE_BYTES + 4 * EpiWarps<EK>::N * EPI_WARP_WORDS * 4 + 1024; }
@@ -758,6 +765,7 @@ static bool g_use_2cta = true;
 static int g_stages = 0;
 static int g_cluster = 2;
 static int g_ablate = 0;
+static bool g_ragged256 = true;
 static std::mutex g_mu;
 
 struct TmKey {
@@ -796,6 +804,7 @@ template <int BN> static int attrs2_all() {
     if (int rc = attr2<BN, EK_PS_ST>()) return rc;
     if (int rc = attr2<BN, EK_BF16_ST>()) return rc;
     if (int rc = attr2<BN, EK_GNIN_ST>()) return rc;
+    if (int rc = attr2<BN, EK_F32_RESBF>()) return rc;
     return attr2<BN, EK_GENERIC>();
 }
 static int set_smem_attrs() {
@@ -828,6 +837,7 @@ int gemm_init() {
     if (const char* st = getenv("VPU_GEMM_STAGES")) g_stages = atoi(st);
     if (const char* cl = getenv("VPU_GEMM_CLUSTER")) g_cluster = atoi(cl) == 4 ? 4 : 2;
     if (const char* ab = getenv("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
+    if (const char* rg = getenv("VPU_GEMM_RAGGED256")) g_ragged256 = rg[0] != '0';
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
@@ -921,7 +931,7 @@ static int epi_kind(const Epi& e) {
     if (e.mode == EPI_PLAIN && e.bias2d && e.bias2d_rows >= 32 && e.out_bf16 && !e.res && e.act == ACT_NONE) return EK_BF16_TAB;
     if (e.mode != EPI_PLAIN || e.bias2d) return EK_GENERIC;
     if (e.out_bf16 && !e.res) return e.act == ACT_GELU ? EK_BF16_GELU : (e.act == ACT_RELU ? EK_BF16_RELU : EK_BF16);
-    if (!e.out_bf16 && e.res && !e.res_bf16 && e.act == ACT_NONE) return EK_F32_RES;
+    if (!e.out_bf16 && e.res && e.act == ACT_NONE) return e.res_bf16 ? EK_F32_RESBF : EK_F32_RES;
     return EK_GENERIC;
 }
 
@@ -937,6 +947,7 @@ static int launch_tc2(const GemmProblem& p, cudaStream_t stream) {
         case EK_PS_ST: return launch_tc2_k<BN, EK_PS_ST>(p, stream);
         case EK_BF16_ST: return launch_tc2_k<BN, EK_BF16_ST>(p, stream);
         case EK_GNIN_ST: return launch_tc2_k<BN, EK_GNIN_ST>(p, stream);
+        case EK_F32_RESBF: return launch_tc2_k<BN, EK_F32_RESBF>(p, stream);
         default: return launch_tc2_k<BN, EK_GENERIC>(p, stream);
     }
 }
@@ -969,6 +980,10 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
     // impl 0: 2-CTA pairs whenever the shape allows it; impl 2 forces the 1-CTA kernel (A/B comparison, tests)
     if (impl == 0 && g_use_2cta && p.epi.mode != EPI_HEAD_FINAL && p.M >= 2 * BM) {
         if (p.N % 256 == 0) return launch_tc2<256>(p, stream);
+        // N = 128 (2k+1), k >= 2 (the DMA image-side K|V|Q projection, N = 1152): 256-wide tiles with a half-empty last tile
+        // (TMA zero-fills the missing weight rows, the epilogue skips the missing columns) waste <= 1/5 of the MMA work but keep
+        // the operand traffic at 64 B/clk/SM; 128-wide tiles need 96 B/clk/SM and run at half the tensor rate (ncu round 1f)
+        if (g_ragged256 && p.N % 128 == 0 && p.N >= 640) return launch_tc2<256>(p, stream);
         if (p.N % 128 == 0) return launch_tc2<128>(p, stream);
     }
     if (p.epi.mode == EPI_HEAD_FINAL) return launch_tc<64, EK_HEAD>(p, stream);
