@@ -169,23 +169,28 @@ __global__ void __launch_bounds__(256) session_crop_kernel(SessionState st, cons
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
+constexpr int FINISH_PIX = 4;      // pixels per thread: 1024 per block, one set of bbox atomics per block
+
 __global__ void __launch_bounds__(256) session_finish_kernel(SessionState st, const int32_t* __restrict__ active, int A,
                                                              const float* __restrict__ logits) {
     pdl_launch_dependents();
     pdl_wait();
+    __shared__ int s_box[4][8];
     const int a = blockIdx.y, s = active[a], T = st.T;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int HW = st.H * st.W;
+    const int32_t* roi = st.roi + 4 * s;
+    const int rmin = roi[0], rmax = roi[1], cmin = roi[2], cmax = roi[3];
+    const float* l0 = logits + (size_t)a * T * T;
+    const float* l1 = logits + (size_t)(A + a) * T * T;
     int fy0 = INT_MAX, fy1 = -1, fx0 = INT_MAX, fx1 = -1;
-    if (idx < HW) {
+#pragma unroll
+    for (int u = 0; u < FINISH_PIX; ++u) {
+        const int idx = (blockIdx.x * FINISH_PIX + u) * 256 + threadIdx.x;
+        if (idx >= HW) break;
         const int Y = idx / st.W, X = idx - Y * st.W;
-        const int32_t* roi = st.roi + 4 * s;
-        const int rmin = roi[0], rmax = roi[1], cmin = roi[2], cmax = roi[3];
         float v = 0.f;
         if (Y >= rmin && Y <= rmax && X >= cmin && X <= cmax) {
             const Tap ty = make_tap(Y - rmin, T, rmax - rmin + 1), tx = make_tap(X - cmin, T, cmax - cmin + 1);
-            const float* l0 = logits + (size_t)a * T * T;
-            const float* l1 = logits + (size_t)(A + a) * T * T;
             // flip.py:21-28 averages the LOGITS of the image and of its mirror, base.py:147-151 applies the sigmoid next
             auto prob = [&](int yy, int xx) {
                 return sigmoid_f(0.5f * (__ldg(l0 + (size_t)yy * T + xx) + __ldg(l1 + (size_t)yy * T + (T - 1 - xx))));
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(256) session_finish_kernel(SessionState st, co
         }
         st.prev_probs[(size_t)s * HW + idx] = v;
         st.pred[(size_t)s * HW + idx] = v > st.pred_thr ? 1 : 0;
-        if (v > st.zoom_thr) { fy0 = fy1 = Y; fx0 = fx1 = X; }
+        if (v > st.zoom_thr) { fy0 = min(fy0, Y); fy1 = max(fy1, Y); fx0 = min(fx0, X); fx1 = max(fx1, X); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -207,9 +212,18 @@ __global__ void __launch_bounds__(256) session_finish_kernel(SessionState st, co
         fx0 = min(fx0, __shfl_xor_sync(0xffffffffu, fx0, o));
         fx1 = max(fx1, __shfl_xor_sync(0xffffffffu, fx1, o));
     }
-    if ((threadIdx.x & 31) == 0 && fy1 >= 0) {
-        int32_t* fb = st.fgbox + 5 * s;
-        atomicMin(fb + 0, fy0); atomicMax(fb + 1, fy1); atomicMin(fb + 2, fx0); atomicMax(fb + 3, fx1); atomicMax(fb + 4, 1);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_box[0][w] = fy0; s_box[1][w] = fy1; s_box[2][w] = fx0; s_box[3][w] = fx1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            fy0 = min(fy0, s_box[0][i]); fy1 = max(fy1, s_box[1][i]); fx0 = min(fx0, s_box[2][i]); fx1 = max(fx1, s_box[3][i]);
+        }
+        if (fy1 >= 0) {
+            int32_t* fb = st.fgbox + 5 * s;
+            atomicMin(fb + 0, fy0); atomicMax(fb + 1, fy1); atomicMin(fb + 2, fx0); atomicMax(fb + 3, fx1); atomicMax(fb + 4, 1);
+        }
     }
 }
 
@@ -240,7 +254,7 @@ int session_prepare_launch(const SessionState& st, const int32_t* active, int A,
 int session_finish_launch(const SessionState& st, const int32_t* active, int A, const float* logits, cudaStream_t stream) {
     if (int rc = check_state(st, active, A)) return rc;
     VPU_REQUIRE(logits, "session_finish: null logits");
-    VPU_CHECK_CUDA(launch_pdl(session_finish_kernel, dim3((st.H * st.W + 255) / 256, A), dim3(256), 0, stream, st, active, A, logits));
+    VPU_CHECK_CUDA(launch_pdl(session_finish_kernel, dim3((st.H * st.W + 256 * FINISH_PIX - 1) / (256 * FINISH_PIX), A), dim3(256), 0, stream, st, active, A, logits));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
