@@ -99,6 +99,9 @@ struct vpu_context {
     int d8() const { return std::max(d.out_dims[1], d.embed_dim / 2); }
     int d32() const { return std::max(d.out_dims[3], d.embed_dim * 2); }
     int group() const { return d.depth == 12 ? 6 : d.depth / 4; }
+    // "vit.ln_fold" = 1: norm1 / norm2 of the ViT blocks are folded into the qkv / fc1 weights (packing.py) and evaluated in the
+    // GEMM epilogues from row statistics the residual GEMMs leave behind (gemm.cuh Epi::ln_*): no LayerNorm pass over the tokens
+    bool ln_fold() const { auto it = scalars.find("vit.ln_fold"); return it != scalars.end() && it->second != 0.f; }
 };
 
 namespace {
@@ -112,6 +115,8 @@ Plan make_plan(const vpu_context& h, int B) {
     p.add("A0", M * h.K0s() * 2);
     p.add("X", M * C * 4);
     p.add("Xn", M * C * 2);
+    p.add("lnstats", M * (size_t)gemm_ln_slots((int)C) * sizeof(float2));
+    p.add("lnrow", M * sizeof(float2));
     p.add("QKV", M * 3 * C * 2);
     p.add("AO", M * C * 2);
     p.add("H", M * 4 * C * 2);
@@ -214,10 +219,19 @@ struct Fwd {
     void set_gn(Epi& e, const Gn& g) {
         e.gn_out = g.out; e.gn_in = g.in; e.gn_wg = g.wg; e.gn_rows = g.rows; e.gn_in_count = (float)g.in_count;
     }
+    // LayerNorm fusion arguments of a ViT GEMM (Epi::ln_*)
+    struct Ln {
+        float2* out = nullptr;
+        __nv_bfloat16* out_bf16 = nullptr;
+        float2* row = nullptr;         // finalised (rstd, mean * rstd) per row, written after a GEMM with `out`
+        const float2* in = nullptr;    // the same buffer on the consuming side
+        const float* s = nullptr;
+        float eps = 1e-6f;
+    };
     // out = act(A W^T + bias [+ tab] [+ res])
     int gemm(const __nv_bfloat16* A, int lda, const std::string& wkey, int M, int Nn, int K, const float* bias, void* out,
              bool out_bf16, int ldo, int act = ACT_NONE, const void* res = nullptr, bool res_bf16 = false, int ldr = 0,
-             const float* tab = nullptr, int tab_rows = 0, const Gn* gn = nullptr) {
+             const float* tab = nullptr, int tab_rows = 0, const Gn* gn = nullptr, const Ln* ln = nullptr) {
         GemmProblem p;
         p.A = A; p.W = Wb(wkey); p.M = M; p.N = Nn; p.K = K; p.lda = lda;
         p.ldw = (int)h.w.at(wkey).shape[1];
@@ -225,8 +239,18 @@ struct Fwd {
         p.epi.out = out; p.epi.out_bf16 = out_bf16; p.epi.ldo = ldo; p.epi.bias = bias; p.epi.act = act;
         p.epi.res = res; p.epi.res_bf16 = res_bf16; p.epi.ldr = ldr; p.epi.bias2d = tab; p.epi.bias2d_rows = tab_rows;
         if (gn) set_gn(p.epi, *gn);
-        const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0));
-        return timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
+        if (ln) {
+            p.epi.ln_out = ln->out; p.epi.ln_out_bf16 = ln->out_bf16; p.epi.ln_in = ln->in; p.epi.ln_s = ln->s;
+            p.epi.ln_slots = gemm_ln_slots(h.C());
+        }
+        const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0)) +
+                          (ln && ln->out ? 2.0 * M * Nn : 0.0);
+        return timed("gemm", 2.0 * M * Nn * K, by, [&] {
+            if (int rc = gemm_launch(p, s, h.gemm_impl)) return rc;
+            if (ln && ln->out)      // finalise the row statistics for the LayerNorm-folded GEMM that follows
+                return ln_rowstats_launch(ln->out, M, p.epi.ln_slots, h.C(), ln->eps, ln->row, s);
+            return 0;
+        });
     }
     int gemm_ps(const __nv_bfloat16* A, const std::string& wkey, const float* bias4, int M, int cout, int K, int g,
                 __nv_bfloat16* out, const Gn* gn = nullptr) {
@@ -315,7 +339,17 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     float* X = f.buf<float>("X");
     RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w", M, C, h.K0s(), nullptr, X, false, C, ACT_NONE, nullptr, false, 0,
                f.Wf("pe.tab"), N));
-    RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w_lo", M, C, h.K0(), nullptr, X, false, C, ACT_NONE, X, false, C));
+    const bool fold = h.ln_fold();
+    typedef Fwd::Ln Ln;
+    float2* lnst = f.buf<float2>("lnstats");
+    bf* X0b = f.buf<bf>("X0b");
+    Ln ln_out;                       // residual GEMMs: fp32 X + bf16 copy + row statistics for the LayerNorm that follows
+    ln_out.out = lnst; ln_out.out_bf16 = f.buf<bf>("Xn"); ln_out.row = f.buf<float2>("lnrow");
+    if (fold)
+        RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w_lo", M, C, h.K0(), f.Wf("pe.zero_b"), X, false, C, ACT_NONE, X, false, C, nullptr, 0,
+                   nullptr, &ln_out));
+    else
+        RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w_lo", M, C, h.K0(), nullptr, X, false, C, ACT_NONE, X, false, C));
 
     // ---- A8-A9: ViT blocks ----
     bf* Xn = f.buf<bf>("Xn");
@@ -330,18 +364,37 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         const std::string k = "blk" + std::to_string(i - 1);
         const bool windowed = (i % h.group()) != 0;
         f.stage = windowed ? "vit_window" : "vit_global";
-        RUN(f.ln(X, k + ".ln1", 1e-6f, M, nullptr, Xn));
-        RUN(f.gemm(Xn, C, k + ".qkv.w", M, 3 * C, C, f.Wf(k + ".qkv.b"), QKV, true, 3 * C));
+        Ln ln_in;
+        ln_in.in = f.buf<float2>("lnrow");
+        if (fold) {
+            ln_in.s = f.Wf(k + ".qkv.s");
+            RUN(f.gemm(Xn, C, k + ".qkv.w", M, 3 * C, C, f.Wf(k + ".qkv.b"), QKV, true, 3 * C, ACT_NONE, nullptr, false, 0, nullptr, 0,
+                       nullptr, &ln_in));
+        } else {
+            RUN(f.ln(X, k + ".ln1", 1e-6f, M, nullptr, Xn));
+            RUN(f.gemm(Xn, C, k + ".qkv.w", M, 3 * C, C, f.Wf(k + ".qkv.b"), QKV, true, 3 * C));
+        }
         if (windowed)
             RUN(f.attn(QKV, 3 * C, 0, QKV, 3 * C, C, QKV, 3 * C, 2 * C, AO, C, win * win, win * win, heads, hd, B * nwin,
                        1.0f / sqrtf((float)hd), true));
         else
             RUN(f.attn(QKV, 3 * C, 0, QKV, 3 * C, C, QKV, 3 * C, 2 * C, AO, C, N, N, heads, hd, B, 1.0f / sqrtf((float)hd),
                        false));
-        RUN(f.gemm(AO, C, k + ".proj.w", M, C, C, f.Wf(k + ".proj.b"), X, false, C, ACT_NONE, X, false, C));
-        RUN(f.ln(X, k + ".ln2", 1e-6f, M, nullptr, Xn));
-        RUN(f.gemm(Xn, C, k + ".fc1.w", M, 4 * C, C, f.Wf(k + ".fc1.b"), Hh, true, 4 * C, ACT_GELU));
-        RUN(f.gemm(Hh, 4 * C, k + ".fc2.w", M, C, 4 * C, f.Wf(k + ".fc2.b"), X, false, C, ACT_NONE, X, false, C));
+        if (fold) {
+            RUN(f.gemm(AO, C, k + ".proj.w", M, C, C, f.Wf(k + ".proj.b"), X, false, C, ACT_NONE, X, false, C, nullptr, 0, nullptr, &ln_out));
+            ln_in.s = f.Wf(k + ".fc1.s");
+            RUN(f.gemm(Xn, C, k + ".fc1.w", M, 4 * C, C, f.Wf(k + ".fc1.b"), Hh, true, 4 * C, ACT_GELU, nullptr, false, 0, nullptr, 0,
+                       nullptr, &ln_in));
+            // the last block's bf16 copy is the DMA stage's key operand
+            Ln lo = ln_out;
+            if (i == h.d.depth) lo.out_bf16 = X0b;
+            RUN(f.gemm(Hh, 4 * C, k + ".fc2.w", M, C, 4 * C, f.Wf(k + ".fc2.b"), X, false, C, ACT_NONE, X, false, C, nullptr, 0, nullptr, &lo));
+        } else {
+            RUN(f.gemm(AO, C, k + ".proj.w", M, C, C, f.Wf(k + ".proj.b"), X, false, C, ACT_NONE, X, false, C));
+            RUN(f.ln(X, k + ".ln2", 1e-6f, M, nullptr, Xn));
+            RUN(f.gemm(Xn, C, k + ".fc1.w", M, 4 * C, C, f.Wf(k + ".fc1.b"), Hh, true, 4 * C, ACT_GELU));
+            RUN(f.gemm(Hh, 4 * C, k + ".fc2.w", M, C, 4 * C, f.Wf(k + ".fc2.b"), X, false, C, ACT_NONE, X, false, C));
+        }
         if (stop_after == i) return 0;
     }
 
@@ -364,13 +417,13 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     bf* QPb = f.buf<bf>("QPb");
     float* Qt = f.buf<float>("Qt");
     float* T = f.buf<float>("T");
-    bf* X0b = f.buf<bf>("X0b");
     bf* Kb = f.buf<bf>("Kb");
     bf* KVQ = f.buf<bf>("KVQ");
     float* rowmax = f.buf<float>("rowmax");
     f.stage = "dma";
     RUN(f.timed("cast", 0, 6.0 * MQ * C, [&] { return cast_add_launch(Q0, nullptr, Q0b, (size_t)MQ * C, s); }));
-    RUN(f.timed("cast", 0, 6.0 * M * C, [&] { return cast_add_launch(X, nullptr, X0b, (size_t)M * C, s); }));
+    if (!fold || stop_after > 0)
+        RUN(f.timed("cast", 0, 6.0 * M * C, [&] { return cast_add_launch(X, nullptr, X0b, (size_t)M * C, s); }));
     const int dh = h.d.dma_heads, Ci = C / 2, dself = C / dh, dcross = Ci / dh;
     const float* Qf = Q0;  // current fp32 queries
     const bf* Kin = X0b;   // current bf16 keys
@@ -544,9 +597,15 @@ std::vector<Need> needed_weights(const vpu_context& h) {
     v.push_back({"pe.w", VPU_BF16, {C, h.K0s()}});
     v.push_back({"pe.w_lo", VPU_BF16, {C, h.K0()}});
     v.push_back({"pe.tab", VPU_F32, {N, C}});
+    if (h.ln_fold()) v.push_back({"pe.zero_b", VPU_F32, {C}});
     for (int i = 0; i < h.d.depth; ++i) {
         const std::string k = "blk" + std::to_string(i);
-        nrm(k + ".ln1", C); nrm(k + ".ln2", C);
+        if (h.ln_fold()) {       // qkv / fc1 hold W diag(gamma) and W beta + b; ".s" = row sums of the bf16 W diag(gamma)
+            v.push_back({k + ".qkv.s", VPU_F32, {3 * C}});
+            v.push_back({k + ".fc1.s", VPU_F32, {4 * C}});
+        } else {
+            nrm(k + ".ln1", C); nrm(k + ".ln2", C);
+        }
         lin(k + ".qkv", 3 * C, C); lin(k + ".proj", C, C); lin(k + ".fc1", 4 * C, C); lin(k + ".fc2", C, 4 * C);
     }
     lin2("ffn", "1", h.d.ppue_ffn_dim, h.ppue_ld());

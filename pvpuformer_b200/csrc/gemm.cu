@@ -214,7 +214,11 @@ enum EpiKind {
     EK_PS_ST = 8,      // EK_PS + statistics
     EK_BF16_ST = 9,    // EK_BF16 + statistics
     EK_GNIN_ST = 10,   // out bf16 = rstd*acc - mean*rstd*wg + bias, + statistics
-    EK_F32_RESBF = 11  // out fp32 = acc + bias + residual bf16       (DMA image<-token out_proj on the bf16 keys)
+    EK_F32_RESBF = 11, // out fp32 = acc + bias + residual bf16       (DMA image<-token out_proj on the bf16 keys)
+    // LayerNorm-fused ViT variants (Epi::ln_*)
+    EK_F32_RES_LNOUT = 12,    // EK_F32_RES + bf16 copy + per-row (sum, sum of squares) slots   (ViT proj / fc2)
+    EK_BF16_LNIN = 13,        // out bf16 = rstd*acc - rstd*mean*s + bias                        (ViT qkv on the un-normalised tokens)
+    EK_BF16_GELU_LNIN = 14    // gelu of the same                                                (ViT fc1)
 };
 
 // measurement-only ablation (VPU_GEMM_ABLATE) is compiled in with -DVPU_GEMM_DEBUG: the check sat in the MMA issue loop
@@ -249,10 +253,12 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
         }
     } else {
         constexpr bool DYN = EK == EK_GENERIC;
-        const bool has_res = DYN ? (e.res != nullptr) : (EK == EK_F32_RES || EK == EK_F32_RESBF);
+        constexpr bool LNOUT = EK == EK_F32_RES_LNOUT;
+        constexpr bool LNIN = EK == EK_BF16_LNIN || EK == EK_BF16_GELU_LNIN;
+        const bool has_res = DYN ? (e.res != nullptr) : (EK == EK_F32_RES || EK == EK_F32_RESBF || LNOUT);
         const bool res_bf16 = DYN ? (e.res_bf16 != 0) : (EK == EK_F32_RESBF);
-        const bool out_bf16 = DYN ? (e.out_bf16 != 0) : (EK != EK_F32_RES && EK != EK_F32_RESBF);
-        const int act = DYN ? e.act : (EK == EK_BF16_GELU ? ACT_GELU : (EK == EK_BF16_RELU ? ACT_RELU : ACT_NONE));
+        const bool out_bf16 = DYN ? (e.out_bf16 != 0) : (EK != EK_F32_RES && EK != EK_F32_RESBF && !LNOUT);
+        const int act = DYN ? e.act : ((EK == EK_BF16_GELU || EK == EK_BF16_GELU_LNIN) ? ACT_GELU : (EK == EK_BF16_RELU ? ACT_RELU : ACT_NONE));
         const bool has_tab = DYN ? (e.bias2d != nullptr) : (EK == EK_BF16_TAB);
         const bool pshuf = DYN ? (e.mode == EPI_PIXEL_SHUFFLE) : (EK == EK_PS || EK == EK_PS_ST);
         const bool stats = DYN ? (e.gn_out != nullptr) : (EK == EK_PS_ST || EK == EK_BF16_ST || EK == EK_GNIN_ST);
@@ -272,6 +278,21 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
             }
         }
         const int sub = lane >> 3, j4 = (lane & 7) * 4;
+        // LayerNorm fusion: this lane's eight rows are r_lo + sub + 4*it
+        float ln_r[8], ln_mr[8], ln_sum[8], ln_sq[8];
+        if constexpr (LNIN) {      // (rstd, mean * rstd) per row, finalised by ln_rowstats_kernel
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int m = r_lo + 4 * it + sub;
+                const float2 t = m < d.M ? __ldg(e.ln_in + m) : make_float2(0.f, 0.f);
+                ln_r[it] = t.x;
+                ln_mr[it] = t.y;
+            }
+        }
+        if constexpr (LNOUT) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { ln_sum[it] = 0.f; ln_sq[it] = 0.f; }
+        }
         // rows of this lane are r_lo + sub + 4*it: the table row and the pixel-shuffle coordinates are divided out
         // once per tile and advanced by 4 per step (run-time divisions per row dominated these epilogues before)
         int trow0 = 0, ps_b0 = 0, ps_i0 = 0, ps_j0 = 0;
@@ -291,6 +312,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), wg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e.bias) bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
             if (gnin) wg = __ldg(reinterpret_cast<const float4*>(e.gn_wg + n));
+            if constexpr (LNIN) wg = __ldg(reinterpret_cast<const float4*>(e.ln_s + n));
             float4 res[8];
             if (has_res) {
 #pragma unroll
@@ -332,6 +354,11 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                         v.x = fmaf(v.x, r, -mr * wg.x); v.y = fmaf(v.y, r, -mr * wg.y);
                         v.z = fmaf(v.z, r, -mr * wg.z); v.w = fmaf(v.w, r, -mr * wg.w);
                     }
+                    if constexpr (LNIN) {
+                        const float r = ln_r[it], mr = ln_mr[it];
+                        v.x = fmaf(v.x, r, -mr * wg.x); v.y = fmaf(v.y, r, -mr * wg.y);
+                        v.z = fmaf(v.z, r, -mr * wg.z); v.w = fmaf(v.w, r, -mr * wg.w);
+                    }
                     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     if (stats) {
                         // one row x four fixed columns: this fp32 partial does not depend on where the sample sits in the batch
@@ -354,6 +381,11 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                         ocol = n - q * e.ps_cout;
                         orow = ((size_t)b * 2 * g + 2 * i + (q >> 1)) * (size_t)(2 * g) + 2 * jx + (q & 1);
                     }
+                    if constexpr (LNOUT) {
+                        ln_sum[it] += (v.x + v.y) + (v.z + v.w);
+                        ln_sq[it] += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+                        *reinterpret_cast<uint2*>(e.ln_out_bf16 + orow * e.ldo + ocol) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                    }
                     if (out_bf16)
                         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + orow * e.ldo + ocol) =
                             make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
@@ -362,6 +394,18 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                 }
             }
             __syncwarp();
+        }
+        if constexpr (LNOUT) {
+            // the 8 lanes that share a row (lane & 7) fold their partials in a fixed butterfly; one slot per (column tile, warp)
+            const int slot = (col_base / BN) * EW + ew;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                float sm = ln_sum[it], sq = ln_sq[it];
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+                const int m = r_lo + 4 * it + sub;
+                if ((lane & 7) == 0 && m < d.M) e.ln_out[(size_t)m * e.ln_slots + slot] = make_float2(sm, sq);
+            }
         }
         if (stats) {
 #pragma unroll
@@ -543,7 +587,7 @@ template <int BN> struct TileCfg2 {
 // shared-memory budget of their staging buffers, one pipeline stage less).
 // The same holds for the K = 384 out_proj of the DMA image<-token attention (6 k-blocks of MMA per 128 KB of fp32 output per CTA:
 // 94 -> 60 us with four).  Four warps per quarter on the neck / table epilogues measured no gain on the whole step.
-template <int EK> struct EpiWarps { static constexpr int N = (EK == EK_BF16_GELU || EK == EK_F32_RESBF) ? 4 : 2; };
+template <int EK> struct EpiWarps { static constexpr int N = (EK == EK_BF16_GELU || EK == EK_BF16_GELU_LNIN || EK == EK_F32_RESBF) ? 4 : 2; };
 template <int EK> __host__ __device__ constexpr int tc2_threads() { return (2 + 4 * EpiWarps<EK>::N) * 32; }
 template <int BN, int EK> __host__ __device__ constexpr int tc2_stages() { return TileCfg2<BN>::STAGES - (EpiWarps<EK>::N > 2 ? 1 : 0); }
 template <int BN, int EK> __host__ __device__ constexpr int tc2_smem() { return tc2_stages<BN, EK>() * TileCfg2<BN>::STAGE_BYTES + 4 * EpiWarps<EK>::N * EPI_WARP_WORDS * 4 + 1024; }
@@ -753,6 +797,33 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(const __nv_bfloat16* __re
     }
 }
 
+// Row statistics of the LayerNorm fusion: the slots a residual GEMM wrote (Epi::ln_out) -> (rstd, mean * rstd) per row, added in
+// slot order in double precision (one thread per row; 2.4 MB in, 0.4 MB out for ViT-B at batch 64).
+__global__ void __launch_bounds__(256) ln_rowstats_kernel(const float2* __restrict__ slots, int M, int P, float inv_c, float eps,
+                                                          float2* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < P; ++k) {
+        const float2 t = __ldg(slots + (size_t)m * P + k);
+        S += (double)t.x; Q += (double)t.y;
+    }
+    const double mean = S * (double)inv_c;
+    const double var = fmax(Q * (double)inv_c - mean * mean, 0.0);
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    out[m] = make_float2(rstd, (float)mean * rstd);
+}
+
+int ln_rowstats_launch(const float2* slots, int M, int P, int C, float eps, float2* out, cudaStream_t stream) {
+    VPU_REQUIRE(slots && out && M > 0 && P > 0 && C > 0, "ln_rowstats: bad argument");
+    VPU_CHECK_CUDA(launch_pdl(ln_rowstats_kernel, dim3((M + 255) / 256), dim3(256), 0, stream, slots, M, P, 1.0f / (float)C, eps, out));
+    VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------
@@ -805,6 +876,9 @@ template <int BN> static int attrs2_all() {
     if (int rc = attr2<BN, EK_BF16_ST>()) return rc;
     if (int rc = attr2<BN, EK_GNIN_ST>()) return rc;
     if (int rc = attr2<BN, EK_F32_RESBF>()) return rc;
+    if (int rc = attr2<BN, EK_F32_RES_LNOUT>()) return rc;
+    if (int rc = attr2<BN, EK_BF16_LNIN>()) return rc;
+    if (int rc = attr2<BN, EK_BF16_GELU_LNIN>()) return rc;
     return attr2<BN, EK_GENERIC>();
 }
 static int set_smem_attrs() {
@@ -921,6 +995,8 @@ static int launch_tc2_k(const GemmProblem& p, cudaStream_t stream) {
 
 // pick the compile-time epilogue the problem's run-time flags describe
 static int epi_kind(const Epi& e) {
+    if (e.ln_out) return EK_F32_RES_LNOUT;                                   // shapes / flags validated in gemm_launch
+    if (e.ln_in) return e.act == ACT_GELU ? EK_BF16_GELU_LNIN : EK_BF16_LNIN;
     if (e.gn_out || e.gn_in) {
         const bool simple = e.out_bf16 && !e.res && !e.bias2d && e.act == ACT_NONE && e.bias && e.gn_out;
         if (simple && e.mode == EPI_PIXEL_SHUFFLE && !e.gn_in && e.ps_g >= 8) return EK_PS_ST;
@@ -948,6 +1024,9 @@ static int launch_tc2(const GemmProblem& p, cudaStream_t stream) {
         case EK_BF16_ST: return launch_tc2_k<BN, EK_BF16_ST>(p, stream);
         case EK_GNIN_ST: return launch_tc2_k<BN, EK_GNIN_ST>(p, stream);
         case EK_F32_RESBF: return launch_tc2_k<BN, EK_F32_RESBF>(p, stream);
+        case EK_F32_RES_LNOUT: return launch_tc2_k<BN, EK_F32_RES_LNOUT>(p, stream);
+        case EK_BF16_LNIN: return launch_tc2_k<BN, EK_BF16_LNIN>(p, stream);
+        case EK_BF16_GELU_LNIN: return launch_tc2_k<BN, EK_BF16_GELU_LNIN>(p, stream);
         default: return launch_tc2_k<BN, EK_GENERIC>(p, stream);
     }
 }
@@ -967,6 +1046,19 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         VPU_REQUIRE(p.epi.gn_rows >= 32 && p.M % p.epi.gn_rows == 0, "GroupNorm-fused GEMM: gn_rows (%d) must be >= 32 and divide M", p.epi.gn_rows);
         VPU_REQUIRE(!p.epi.gn_in || (p.epi.gn_wg && p.epi.gn_in_count > 0.f), "GroupNorm-fused GEMM: gn_in needs gn_wg and gn_in_count");
         VPU_REQUIRE(p.epi.mode != EPI_HEAD_FINAL, "GroupNorm fusion is not available in the head-final epilogue");
+    }
+    if (p.epi.ln_out || p.epi.ln_in) {
+        const Epi& e = p.epi;
+        VPU_REQUIRE(impl == 0 && g_use_2cta && p.M >= 2 * BM && p.N % 256 == 0 && e.mode == EPI_PLAIN && !e.bias2d && !e.gn_in && !e.gn_out,
+                    "LayerNorm-fused GEMM needs the 2-CTA kernel, N %% 256 == 0 and a plain epilogue (M=%d N=%d)", p.M, p.N);
+        VPU_REQUIRE(e.ln_slots > 0 && e.bias, "LayerNorm-fused GEMM: ln_slots / bias missing");
+        if (e.ln_out)
+            VPU_REQUIRE(!e.ln_in && !e.out_bf16 && e.res && !e.res_bf16 && e.act == ACT_NONE && e.ln_out_bf16 && e.ln_slots == gemm_ln_slots(p.N),
+                        "ln_out needs a fp32 output with fp32 residual, a bf16 copy buffer and ln_slots == %d", gemm_ln_slots(p.N));
+        else
+            VPU_REQUIRE(e.out_bf16 && !e.res && e.ln_s && (e.act == ACT_NONE || e.act == ACT_GELU),
+                        "ln_in needs a bf16 output without residual and ln_s");
+        return launch_tc2<256>(p, stream);
     }
     if (impl == 1) {
         GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};

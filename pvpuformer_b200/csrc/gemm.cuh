@@ -47,7 +47,25 @@ struct Epi {
     const float* gn_wg = nullptr;
     int gn_rows = 0;
     float gn_in_count = 0.f;
+    // LayerNorm fusion for the ViT blocks (reference models_vit.py:72-75: x + attn(norm1(x)), x + mlp(norm2(x))).
+    //   ln_out      [M][ln_slots] (sum, sum of squares) of the fp32 rows this GEMM writes (the residual stream), one slot per
+    //               (256-column tile, epilogue warp): every slot is written exactly once, by fixed threads in a fixed order, and
+    //               the reader adds the slots in index order -- no atomics, bit-identical from run to run and for any batch
+    //   ln_out_bf16 bf16 copy of the same rows [M, ldo]: the A operand of the next GEMM
+    //   ln_in       [M] (rstd, mean * rstd) of the rows the A operand holds un-normalised (ln_rowstats_launch turns the slots
+    //               into this).  The weights bound for this GEMM are W' = W diag(gamma), bias = W beta + b,
+    //               ln_s[n] = sum_k W'[n, k] (of the bf16-rounded W'), so that  LN(x) W^T + b = rstd (x W'^T) - rstd mean ln_s + bias
+    float2* ln_out = nullptr;
+    __nv_bfloat16* ln_out_bf16 = nullptr;
+    const float2* ln_in = nullptr;
+    const float* ln_s = nullptr;
+    int ln_slots = 0;
 };
+
+// slots per row of Epi::ln_out for an N-column residual GEMM (256-wide tiles x 2 epilogue warps per TMEM lane quarter)
+inline int gemm_ln_slots(int N) { return ((N + 255) / 256) * 2; }
+// slots [M][P] -> (rstd, mean * rstd) [M] of a LayerNorm over C values with the given eps
+int ln_rowstats_launch(const float2* slots, int M, int P, int C, float eps, float2* out, cudaStream_t stream);
 
 struct GemmProblem {
     const __nv_bfloat16* A = nullptr;  // [M, lda]

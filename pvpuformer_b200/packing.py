@@ -14,9 +14,13 @@ Algebraic folds, each exact in real arithmetic:
   * ConvTranspose2d(k=2,s=2) / Conv2d(k=2,s=2) (is_vpu_model.py:56-86) reshaped to plain GEMM
     weights with (kh, kw) folded into N resp. K;
   * the head's fusion 1x1 conv split into four [256,256] slices (it commutes with the bilinear
-    resize, swin_transformer.py:727-737).
+    resize, swin_transformer.py:727-737);
+  * norm1 / norm2 of every ViT block (models_vit.py:72-75) folded into the qkv / fc1 weights: W' = W diag(gamma),
+    b' = W beta + b, and the per-row mean / rstd are applied in the GEMM epilogue from statistics the preceding residual
+    GEMM wrote (VPU_LN_FOLD=0 keeps the separate LayerNorm pass for A/B measurements).
 """
 import math
+import os
 
 import torch
 
@@ -72,13 +76,28 @@ def pack_weights(sd, cfg, device):
     tab = f["backbone.pos_embed"][0, 1:] + (f["backbone.patch_embed.proj.bias"] + f["patch_embed_coords.proj.bias"] - fold)
     F32("pe.tab", tab)
 
+    def lin_ln(dst, src, ln):     # Linear applied to LayerNorm(x) with x stored un-normalised (gemm.cuh Epi::ln_in):
+        w = f[src + ".weight"]    #   W (gamma (x - mean) rstd + beta) + b = rstd (W' x) - mean rstd rowsum(W') + (W beta + b)
+        wq = (w * f[ln + ".weight"].view(1, -1)).to(bf)
+        out[dst + ".w"] = wq.contiguous()
+        F32(dst + ".s", wq.float().sum(dim=1))                                # row sums of the ROUNDED W': consistent with the MMA
+        F32(dst + ".b", w @ f[ln + ".bias"] + f[src + ".bias"])
+
+    ln_fold = os.environ.get("VPU_LN_FOLD", "1") != "0"
+    scalars["vit.ln_fold"] = 1.0 if ln_fold else 0.0
+    if ln_fold:
+        F32("pe.zero_b", torch.zeros(C, device=device))
     for i in range(cfg.depth):
         s, d = "backbone.blocks.%d" % i, "blk%d" % i
-        norm(d + ".ln1", s + ".norm1")
-        norm(d + ".ln2", s + ".norm2")
-        lin(d + ".qkv", s + ".attn.qkv")
+        if ln_fold:
+            lin_ln(d + ".qkv", s + ".attn.qkv", s + ".norm1")
+            lin_ln(d + ".fc1", s + ".mlp.fc1", s + ".norm2")
+        else:
+            norm(d + ".ln1", s + ".norm1")
+            norm(d + ".ln2", s + ".norm2")
+            lin(d + ".qkv", s + ".attn.qkv")
+            lin(d + ".fc1", s + ".mlp.fc1")
         lin(d + ".proj", s + ".attn.proj")
-        lin(d + ".fc1", s + ".mlp.fc1")
         lin(d + ".fc2", s + ".mlp.fc2")
 
     # ---- PPuE FFN (K = 899 padded to a multiple of 8 with zero columns) ----
