@@ -9,7 +9,10 @@ same `forward(image, points, prompts, as_prompt_type, edloss, pclout) -> {'insta
 torch only owns memory and streams.  There is no fallback: without the extension or on a
 non-sm_100 device the forward raises.
 """
+import copy
 import ctypes
+import functools
+import inspect
 import random
 
 import numpy as np
@@ -41,18 +44,40 @@ def _register(root, dotted, tensor, kind):
         m.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
 
 
+REFERENCE_CLASS = "isegm.model.is_vpu_model.VitMultiGaussianVector_ed_Model"
+
+
+def _record_config(init):
+    """What the reference's @serialize decorator records (utils/serialization.py:7-41): `_config` = {'class': dotted name of
+    the reference class, 'params': {name: {'type': 'builtin' | 'class', 'value', 'specified'}}} for every constructor
+    argument, so that `save_checkpoint` (utils/misc.py:31-33) writes a checkpoint either implementation loads."""
+    names = list(inspect.signature(init).parameters)[1:]
+    defaults = {k: v.default for k, v in inspect.signature(init).parameters.items() if v.default is not inspect.Parameter.empty}
+
+    @functools.wraps(init)
+    def new_init(self, *args, **kwargs):
+        params = copy.deepcopy(kwargs)
+        params.update(zip(names, args))
+        specified = set(params)
+        for k, v in defaults.items():
+            params.setdefault(k, v)
+        cfg = {"class": REFERENCE_CLASS, "params": {}}
+        for k, v in params.items():
+            is_class = inspect.isclass(v)
+            cfg["params"][k] = {"type": "class" if is_class else "builtin",
+                                "value": (v.__module__ + "." + v.__qualname__) if is_class else v, "specified": k in specified}
+        self._config = cfg
+        init(self, *args, **kwargs)
+    return new_init
+
+
 class VitMultiGaussianVector_ed_Model(nn.Module):
+    @_record_config
     def __init__(self, num_max_points=24, backbone_params={}, neck_params={}, head_params={}, random_split=False,
                  residual=False, with_aux_output=False, norm_radius=5, use_disks=False, cpu_dist_maps=False,
                  use_rgb_conv=False, use_leaky_relu=False, with_prev_mask=False,
                  norm_mean_std=([.485, .456, .406], [.229, .224, .225])):
         super().__init__()
-        # what the reference's @serialize decorator records (utils/serialization.py:7-41)
-        self._config = {"class": "isegm.model.is_vpu_model.VitMultiGaussianVector_ed_Model",
-                        "params": dict(num_max_points=num_max_points, backbone_params=backbone_params,
-                                       neck_params=neck_params, head_params=head_params, random_split=random_split,
-                                       residual=residual, with_aux_output=with_aux_output, norm_radius=norm_radius,
-                                       use_disks=use_disks, with_prev_mask=with_prev_mask)}
         if random_split:
             raise NotImplementedError("random_split=True (token shuffle, models_vit.py:266-272) is outside the B200 path")
         if not (use_disks and with_prev_mask) or cpu_dist_maps or use_rgb_conv:
