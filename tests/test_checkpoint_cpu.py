@@ -70,3 +70,13 @@ def test_checkpoint_written_by_the_reference_loads_and_resamples_like_the_refere
     ref_interp(ref.backbone, a)
     ck.interpolate_pos_embed(m.backbone, b)
     assert torch.equal(a["pos_embed"], b["pos_embed"])
+
+
+@pytest.mark.reference
+def test_checkpoint_written_here_loads_in_the_reference():
+    rh.import_reference()
+    from isegm.utils.serialization import load_model as ref_load_model
+    m = build_model("vit_base", state_dict=synthetic_state_dict(make_config("vit_base"), 1))
+    r = ref_load_model(m._config, False)
+    r.load_state_dict(m.state_dict(), strict=True)
+    assert type(r).__name__ == "VitMultiGaussianVector_ed_Model" and r.with_prev_mask
