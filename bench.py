@@ -310,7 +310,7 @@ def main():
     # DRAM bytes per launch of the GEMM class from the committed ncu capture of this same command (profiles/, tools/ncu_traffic.py);
     # the algorithmic bytes per launch (operands + outputs once) are booked live by the C ABI next to the FLOPs
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "gemm_traffic_r1.json")
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic_r1f.json")
     if os.path.exists(tpath) and args.arch == "vit_base" and B == 64 and not args.no_aux:
         traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
     n_gemm = sum(c["launches"] for c in gemm) or 1

@@ -245,12 +245,11 @@ struct Fwd {
         }
         const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0)) +
                           (ln && ln->out ? 2.0 * M * Nn : 0.0);
-        return timed("gemm", 2.0 * M * Nn * K, by, [&] {
-            if (int rc = gemm_launch(p, s, h.gemm_impl)) return rc;
-            if (ln && ln->out)      // finalise the row statistics for the LayerNorm-folded GEMM that follows
-                return ln_rowstats_launch(ln->out, M, p.epi.ln_slots, h.C(), ln->eps, ln->row, s);
-            return 0;
-        });
+        if (int rc = timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); })) return rc;
+        if (ln && ln->out)      // finalise the row statistics for the LayerNorm-folded GEMM that follows
+            return timed("lnstats", 0, (double)M * (p.epi.ln_slots + 1) * 8.0,
+                         [&] { return ln_rowstats_launch(ln->out, M, p.epi.ln_slots, h.C(), ln->eps, ln->row, s); });
+        return 0;
     }
     int gemm_ps(const __nv_bfloat16* A, const std::string& wkey, const float* bias4, int M, int cout, int K, int g,
                 __nv_bfloat16* out, const Gn* gn = nullptr) {
