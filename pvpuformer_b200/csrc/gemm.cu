@@ -587,7 +587,13 @@ template <int BN> struct TileCfg2 {
 // shared-memory budget of their staging buffers, one pipeline stage less).
 // The same holds for the K = 384 out_proj of the DMA image<-token attention (6 k-blocks of MMA per 128 KB of fp32 output per CTA:
 // 94 -> 60 us with four).  Four warps per quarter on the neck / table epilogues measured no gain on the whole step.
-template <int EK> struct EpiWarps { static constexpr int N = (EK == EK_BF16_GELU || EK == EK_BF16_GELU_LNIN || EK == EK_F32_RESBF) ? 4 : 2; };
+#ifndef VPU_EPI_VARIANT
+#define VPU_EPI_VARIANT 0
+#endif
+template <int EK> struct EpiWarps {
+    static constexpr int N = (EK == EK_BF16_GELU || EK == EK_BF16_GELU_LNIN || EK == EK_F32_RESBF ||
+                              (VPU_EPI_VARIANT >= 1 && EK == EK_F32_RES_LNOUT) || (VPU_EPI_VARIANT >= 2 && EK == EK_BF16_LNIN)) ? 4 : 2;
+};
 template <int EK> __host__ __device__ constexpr int tc2_threads() { return (2 + 4 * EpiWarps<EK>::N) * 32; }
 template <int BN, int EK> __host__ __device__ constexpr int tc2_stages() { return TileCfg2<BN>::STAGES - (EpiWarps<EK>::N > 2 ? 1 : 0); }
 template <int BN, int EK> __host__ __device__ constexpr int tc2_smem() { return tc2_stages<BN, EK>() * TileCfg2<BN>::STAGE_BYTES + 4 * EpiWarps<EK>::N * EPI_WARP_WORDS * 4 + 1024; }
@@ -796,6 +802,8 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(const __nv_bfloat16* __re
         }
     }
 }
+
+int gemm_ln_slots(int N) { return ((N + 255) / 256) * EpiWarps<EK_F32_RES_LNOUT>::N; }
 
 // Row statistics of the LayerNorm fusion: the slots a residual GEMM wrote (Epi::ln_out) -> (rstd, mean * rstd) per row, added in
 // slot order in double precision (one thread per row; 2.4 MB in, 0.4 MB out for ViT-B at batch 64).

@@ -62,8 +62,8 @@ struct Epi {
     int ln_slots = 0;
 };
 
-// slots per row of Epi::ln_out for an N-column residual GEMM (256-wide tiles x 2 epilogue warps per TMEM lane quarter)
-inline int gemm_ln_slots(int N) { return ((N + 255) / 256) * 2; }
+// slots per row of Epi::ln_out for an N-column residual GEMM (256-wide tiles x epilogue warps per TMEM lane quarter)
+int gemm_ln_slots(int N);
 // slots [M][P] -> (rstd, mean * rstd) [M] of a LayerNorm over C values with the given eps
 int ln_rowstats_launch(const float2* slots, int M, int P, int C, float eps, float2* out, cudaStream_t stream);
 
