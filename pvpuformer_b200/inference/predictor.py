@@ -8,8 +8,8 @@ exactly prepare -> net -> finish.
 
 Prompt simulation: the reference rebuilds box and scribble prompts on the host at every click
 (engine/trainer.py:703-768) even though `as_prompt_type == 0` never reads them.  Here click-only prediction passes
-prompts=None; for prompt types 1/2 the caller supplies `prompt_fn(prev_mask_roi, gt_mask_roi, points_nd) -> prompts`
-(the simulators are SURVEY.md 8(f) rank 3, not part of this path).
+prompts=None; for prompt types 1/2 `prompt_fn(prev_mask_roi, gt_mask_roi, points_nd) -> prompts` is called, by default
+the restated simulators of inference/prompts.py (`eval_prompt_fn`).
 """
 import numpy as np
 import torch
@@ -192,5 +192,7 @@ def vpu_eval_predictor(net, device, prompt_fn=None):
     fixed 448x448 zoom-in with skip_clicks=-1, one cascade step on the first click."""
     p = get_predictor(net, "NoBRS", device, with_flip=True, zoom_in_params={"skip_clicks": -1, "target_size": (448, 448)},
                       predictor_params={"cascade_step": 1, "cascade_adaptive": False, "cascade_clicks": 1})
+    if prompt_fn is None:
+        from .prompts import eval_prompt_fn as prompt_fn
     p.prompt_fn = prompt_fn
     return p

@@ -122,6 +122,65 @@ def test_noc_loop_matches_reference_plumbing():
     assert ref_utils.compute_noc_metric(ious, [0.8, 0.85, 0.9], max_clicks=20)[0] == compute_noc_metric(ious, [0.8, 0.85, 0.9], 20)[0]
 
 
+class PromptNet(FakeNet):
+    """FakeNet + a term that depends on the box / scribble prompt, so a wrong prompt changes the masks and the clicks."""
+
+    def forward(self, image, points, prompts=None, as_prompt_type=0):
+        out = super().forward(image, points)["instances"]
+        if as_prompt_type == 1:
+            boxes = prompts[1].double()
+            out = out + (0.4 * (boxes[:, :4].sum(dim=1) % 97) / 97).view(-1, 1, 1, 1).float()
+        elif as_prompt_type == 2:
+            scr = torch.as_tensor(np.asarray(prompts[2][0], dtype=np.float64))
+            out = out + (0.4 * (scr.sum(dim=(1, 2, 3)) % 97) / 97).view(-1, 1, 1, 1).float()
+        return {"instances": out, "instances_aux": None}
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("as_prompt_type", [1, 2])
+def test_noc_loop_with_simulated_box_and_scribble_prompts_matches_reference(as_prompt_type):
+    """Box / scribble prompts rebuilt at every click by the restated simulators (inference/prompts.py) inside this repo's
+    predictor against the reference's predictor calling its own get_next_promts: same random seeds, same clicks and IoUs."""
+    import random
+    from oracle import ref_harness as rh
+    rh.import_reference()
+    from isegm.inference.predictors import get_predictor as ref_get_predictor
+    from isegm.inference.clicker import Clicker as RefClicker
+    from isegm.inference.utils import get_iou as ref_get_iou
+
+    def ref_evaluate_sample(image, gt_mask, predictor, max_iou_thr, max_clicks, as_prompt_type):
+        # isegm/inference/vpu_evaluation.py:35-98 with its hard-coded `as_prompt_type = 0` (:48) turned into the argument
+        clicker, pred_mask, ious = RefClicker(gt_mask=gt_mask), np.zeros_like(gt_mask), []
+        with torch.no_grad():
+            predictor.set_input_image(image)
+            for click_indx in range(max_clicks):
+                clicker.make_next_click(pred_mask)
+                pred_probs, _ = predictor.get_vqu_prediction(clicker, gt_mask=gt_mask, as_prompt_type=as_prompt_type,
+                                                             click_indx=click_indx, as_multi_prompts=True)
+                pred_mask = pred_probs > 0.49
+                ious.append(ref_get_iou(gt_mask, pred_mask))
+                if ious[-1] >= max_iou_thr:
+                    break
+        return clicker.clicks_list, np.array(ious, dtype=np.float32), pred_probs
+
+    net = PromptNet()
+    for image, gt in _samples(2, seed0=20):
+        out = []
+        for impl in ("ref", "here"):
+            random.seed(5)
+            np.random.seed(5)
+            if impl == "ref":
+                pred = ref_get_predictor(net, "NoBRS", "cpu", with_flip=True, zoom_in_params={"skip_clicks": -1, "target_size": (448, 448)},
+                                         predictor_params={"cascade_step": 1, "cascade_adaptive": False, "cascade_clicks": 1})
+                clicks, ious, probs = ref_evaluate_sample(image, gt, pred, 0.95, max_clicks=4, as_prompt_type=as_prompt_type)
+            else:
+                clicks, ious, probs = evaluate_sample(image, gt, vpu_eval_predictor(net, "cpu"), 0.95, max_clicks=4,
+                                                      as_prompt_type=as_prompt_type)
+            out.append(([(bool(c.is_positive), int(c.coords[0]), int(c.coords[1])) for c in clicks], ious, probs))
+        assert out[0][0] == out[1][0]
+        assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
 def _worker(rank, world, port, n_images, out_q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
