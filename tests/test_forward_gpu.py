@@ -89,6 +89,29 @@ def test_forward_vs_reference_golden_vit_base(name):
     _rel_gates(got, ref)
 
 
+@pytest.mark.parametrize("name", ["vit_large_box", "vit_large_scribble"])
+def test_forward_vs_reference_golden_vit_large_mixed_prompts(name):
+    """ViT-Large with box / scribble prompts through PPuE."""
+    m, _ = _model("vit_large")
+    image4, points, prompts, t = gu.case_inputs(name)
+    g = gu.load(name)
+    B = image4.shape[0]
+    gu.seed_scribble()
+    rows = m.ppue(points.cuda(), _to_dev(prompts), t).cpu().numpy()
+    assert np.array_equal(rows != 0, g["ppue"] != 0) and np.abs(rows - g["ppue"]).max() <= 1e-5
+    gu.seed_scribble()
+    cf = m.coord_features(image4.cuda(), points.cuda(), _to_dev(prompts), t).cpu().numpy()
+    assert np.array_equal(cf[:, 1:].astype(np.uint8), gu.unpack_disks(g, B))
+    gu.seed_scribble()
+    out = m(image4.cuda(), points.cuda(), _to_dev(prompts), t)
+    inst, aux = out["instances"].cpu(), out["instances_aux"].cpu()
+    assert np.abs(inst[:, :, ::4, ::4].numpy() - g["instances_s4"]).max() <= LOGIT_TOL
+    assert np.abs(aux[:, [0, 24], ::8, ::8].numpy() - g["aux_s8_sel"]).max() <= AUX_TOL
+    ref, got = torch.from_numpy(g["instances_s4"]), inst[:, :, ::4, ::4]
+    assert _iou(torch.sigmoid(got) > 0.49, torch.sigmoid(ref) > 0.49) >= 0.999
+    _rel_gates(got, ref)
+
+
 @pytest.mark.parametrize("arch", ["vit_large", "vit_huge"])
 def test_forward_vs_reference_golden_large_huge(arch):
     m, _ = _model(arch)

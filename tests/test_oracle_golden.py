@@ -45,6 +45,25 @@ def test_oracle_matches_reference_golden_vit_base(name):
     assert np.abs(taps["q_out"][:, :, ::16].numpy() - g["q_out_slice"]).max() < 1e-3
 
 
+@pytest.mark.parametrize("name", ["vit_large_box", "vit_large_scribble"])
+def test_oracle_matches_reference_golden_vit_large_mixed_prompts(name):
+    """ViT-Large with box / scribble prompts through PPuE."""
+    cfg = make_config("vit_large")
+    image4, points, prompts, t = gu.case_inputs(name)
+    g = gu.load(name)
+    taps = {}
+    gu.seed_scribble()
+    with torch.no_grad():
+        out = vo.forward(_sd("vit_large"), cfg, image4, points, prompts, t, taps=taps)
+    B = image4.shape[0]
+    assert np.array_equal(taps["coord_features"][:, 1:].numpy().astype(np.uint8), gu.unpack_disks(g, B))
+    assert np.array_equal(taps["ppue"].float().numpy() != 0, g["ppue"] != 0)
+    assert np.abs(taps["ppue"].float().numpy() - g["ppue"]).max() <= 1e-5
+    assert np.abs(taps["seg_lowres"].numpy() - g["seg_lowres"]).max() < 1e-4
+    assert np.abs(out["instances"][:, :, ::4, ::4].numpy() - g["instances_s4"]).max() < 1e-4
+    assert np.abs(out["instances_aux"][:, [0, 24], ::8, ::8].numpy() - g["aux_s8_sel"]).max() < 1e-4
+
+
 @pytest.mark.parametrize("arch", ["vit_large", "vit_huge"])
 def test_oracle_matches_reference_golden_large_huge(arch):
     cfg = make_config(arch)
