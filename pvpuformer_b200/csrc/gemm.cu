@@ -295,11 +295,23 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
         }
         // rows of this lane are r_lo + sub + 4*it: the table row and the pixel-shuffle coordinates are divided out
         // once per tile and advanced by 4 per step (run-time divisions per row dominated these epilogues before)
-        int trow0 = 0, ps_b0 = 0, ps_i0 = 0, ps_j0 = 0;
+        int trow0 = 0;
         if (has_tab) trow0 = (r_lo + sub) % e.bias2d_rows;
+        // pixel shuffle: input row m = (b, i, j) -> output row (b, 2i + kh, 2j + kw) = ps_base + kh * 2g + kw.  The row part is
+        // worked out once per tile for the lane's eight rows (they advance by 4 with at most g / 4 carries); the (kh, kw, channel)
+        // part is uniform over a 32-column chunk (cout % 32 == 0).  Doing both per row and per chunk -- divergent carry loops and
+        // an integer division inside the store loop -- cost 73 / 167 us on the neck's ConvTranspose GEMMs (tools/gemm_ps_ab.py).
+        int ps_base[8];
         if (pshuf) {
-            const int m0 = r_lo + sub, gg = e.ps_g * e.ps_g, ij = m0 % gg;
-            ps_b0 = m0 / gg; ps_i0 = ij / e.ps_g; ps_j0 = ij % e.ps_g;
+            const int g = e.ps_g, m0 = r_lo + sub, gg = g * g, ij = m0 % gg;
+            int b = m0 / gg, i = ij / g, jx = ij % g;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                ps_base[it] = (b * 2 * g + 2 * i) * (2 * g) + 2 * jx;
+                jx += 4;
+                while (jx >= g) { jx -= g; ++i; }      // g >= 8 on the compile-time paths: at most one carry per step
+                while (i >= g) { i -= g; ++b; }
+            }
         }
 #pragma unroll 1
         for (int c = ew * 32; c < BN; c += EW * 32) {
@@ -308,6 +320,12 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
             uint32_t r[32];
             tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
             const int n = n0 + j4;
+            int ps_qoff = 0, ps_ocol = 0;
+            if (pshuf) {
+                const int q = n0 / e.ps_cout;                  // warp-uniform: a chunk never straddles two (kh, kw) blocks
+                ps_qoff = (q >> 1) * 2 * e.ps_g + (q & 1);
+                ps_ocol = n - q * e.ps_cout;
+            }
             // operands that do not depend on the accumulator are requested while the TMEM load is in flight
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), wg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e.bias) bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
@@ -372,15 +390,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                     else if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     size_t orow = (size_t)m;
                     int ocol = n;
-                    if (pshuf) {
-                        const int g = e.ps_g;
-                        int jx = ps_j0 + 4 * it, i = ps_i0, b = ps_b0;      // g >= 4 rows per grid line: carries by subtraction
-                        while (jx >= g) { jx -= g; ++i; }
-                        while (i >= g) { i -= g; ++b; }
-                        const int q = n / e.ps_cout;
-                        ocol = n - q * e.ps_cout;
-                        orow = ((size_t)b * 2 * g + 2 * i + (q >> 1)) * (size_t)(2 * g) + 2 * jx + (q & 1);
-                    }
+                    if (pshuf) { orow = (size_t)(ps_base[it] + ps_qoff); ocol = ps_ocol; }
                     if constexpr (LNOUT) {
                         ln_sum[it] += (v.x + v.y) + (v.z + v.w);
                         ln_sq[it] += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
