@@ -601,11 +601,12 @@ template <int BN> struct TileCfg2 {
 #define VPU_EPI_VARIANT 0
 #endif
 template <int EK> struct EpiWarps {
-    static constexpr int N = (EK == EK_BF16_GELU || EK == EK_BF16_GELU_LNIN || EK == EK_F32_RESBF ||
-                              (VPU_EPI_VARIANT >= 1 && EK == EK_F32_RES_LNOUT) || (VPU_EPI_VARIANT >= 2 && EK == EK_BF16_LNIN)) ? 4 : 2;
+    static constexpr int N = (EK == EK_BF16_GELU || EK == EK_BF16_GELU_LNIN || EK == EK_F32_RESBF) ? 4 :
+                             ((VPU_EPI_VARIANT >= 1 && EK == EK_F32_RES_LNOUT) || (VPU_EPI_VARIANT >= 2 && EK == EK_F32_RES) ||
+                              (VPU_EPI_VARIANT >= 3 && EK == EK_BF16_LNIN)) ? 3 : 2;
 };
 template <int EK> __host__ __device__ constexpr int tc2_threads() { return (2 + 4 * EpiWarps<EK>::N) * 32; }
-template <int BN, int EK> __host__ __device__ constexpr int tc2_stages() { return TileCfg2<BN>::STAGES - (EpiWarps<EK>::N > 2 ? 1 : 0); }
+template <int BN, int EK> __host__ __device__ constexpr int tc2_stages() { return TileCfg2<BN>::STAGES - (EpiWarps<EK>::N > 3 ? 1 : 0); }   // 3 per quarter still fit 5 stages (220 KB)
 template <int BN, int EK> __host__ __device__ constexpr int tc2_smem() { return tc2_stages<BN, EK>() * TileCfg2<BN>::STAGE_BYTES + 4 * EpiWarps<EK>::N * EPI_WARP_WORDS * 4 + 1024; }
 
 template <int BN, int EK, int CL>   // CL = CTAs per cluster: 2 (one MMA pair) or 4 (two pairs sharing the B tile by TMA multicast)
