@@ -14,6 +14,7 @@
 #include "gemm.cuh"
 #include "noc.cuh"
 #include "prompt.cuh"
+#include "raster.cuh"
 #include "session.cuh"
 
 namespace vpu {
@@ -874,6 +875,13 @@ int vpu_noc_next_clicks(const int8_t* gt, const uint8_t* pred, uint8_t* not_clic
     VPU_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vpu_noc_next_clicks: workspace must be 256-byte aligned");
     return noc_next_clicks_launch(gt, pred, not_clicked, S, H, W, clicks, reinterpret_cast<long long*>(iou_counts), workspace,
                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_raster_prompts(int type, const int32_t* boxes, const int32_t* scribbles, int S, int n, int B, int size, uint8_t* planes,
+                       void* stream) {
+    RasterArgs a;
+    a.type = type; a.boxes = boxes; a.scribbles = scribbles; a.S = S; a.n = n; a.size = size; a.planes = planes;
+    return raster_prompts_launch(a, B, reinterpret_cast<cudaStream_t>(stream));
 }
 
 static SessionState to_session(const vpu_session_state* st) {

@@ -4,10 +4,10 @@
   with Python's global `random` (reference isegm/model/ops.py:271-295), so reproducing its output
   for a given `random.seed` means consuming `random.randint` in exactly its order on the host.
   Only the integer selection happens here; the Gaussian values are evaluated on the device.
-* box / scribble rasterisation into the click planes: one `cv2.rectangle` / `cv2.polylines`
-  (thickness 3) per sample, exactly the calls of reference isegm/model/is_model.py:97-146
-  (bit-exactness is defined against OpenCV's fixed-point thick-line fill; SURVEY.md 8f rank 4
-  lists a native rasteriser as a later row).
+* box / scribble rasterisation into the click planes for prompts with vertices OUTSIDE the image: one
+  `cv2.rectangle` / `cv2.polylines` (thickness 3) per sample, exactly the calls of reference
+  isegm/model/is_model.py:97-146.  Prompts inside the image (everything the reference's simulators produce)
+  are rasterised on the device by csrc/raster.cu, which restates OpenCV's fixed-point thick-line fill bit for bit.
 """
 import random
 
@@ -49,6 +49,14 @@ def scribble_slots(ppue_points_cpu, n):
         if len(valid):
             out[b] = valid[-1]
     return out
+
+
+def box_corners_inside(boxes_cpu, size=448):
+    """True if every box outline has its four corners inside the image (then csrc/raster.cu reproduces cv2.rectangle exactly)."""
+    b = np.asarray(boxes_cpu).astype(np.int64)
+    x0, x1 = b[:, 0] - b[:, 2] // 2, b[:, 0] + b[:, 2] // 2
+    y0, y1 = b[:, 1] - b[:, 3] // 2, b[:, 1] + b[:, 3] // 2
+    return bool(min(x0.min(), x1.min(), y0.min(), y1.min()) >= 0 and max(x0.max(), x1.max(), y0.max(), y1.max()) < size)
 
 
 def raster_planes(as_prompt_type, boxes_cpu, scribbles, n, B, size=448):

@@ -63,6 +63,7 @@ SIGNATURES = {
                               c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "vpu_noc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vpu_noc_next_clicks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vpu_raster_prompts": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vpu_session_prepare": (c_int, [POINTER(VpuSessionState), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpu_session_finish": (c_int, [POINTER(VpuSessionState), c_void_p, c_int, c_void_p, c_void_p]),
     "vpu_debug_attention_trace": (c_int, [c_void_p, c_int]),

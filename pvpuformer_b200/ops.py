@@ -92,3 +92,15 @@ def noc_next_clicks(gt, pred, not_clicked, workspace=None):
     L.check(lib.vpu_noc_next_clicks(L.ptr(gt), L.ptr(pred), L.ptr(not_clicked), S, H, W, L.ptr(clicks), L.ptr(counts), L.ptr(workspace),
                                     workspace.numel(), L.current_stream()))
     return clicks, counts
+
+
+def raster_prompts(as_prompt_type, boxes, scribbles, n, B, size=448, device=None):
+    """Box / scribble outline planes uint8 [B,2,size,size] (csrc/raster.cu; reference is_model.py:97-146 through cv2).
+    boxes: int32 cuda [B,5]; scribbles: int32 cuda [B,S,2] (x, y).  Vertices must lie inside the image (checked by the caller)."""
+    dev = device or (boxes.device if as_prompt_type == 1 else scribbles.device)
+    planes = torch.empty(B, 2, size, size, dtype=torch.uint8, device=dev)
+    S = 0 if as_prompt_type == 1 else scribbles.shape[1]
+    L.check(L.load().vpu_raster_prompts(int(as_prompt_type), L.ptr(boxes) if as_prompt_type == 1 else None,
+                                        L.ptr(scribbles) if as_prompt_type == 2 else None, S, n, B, size, L.ptr(planes),
+                                        L.current_stream()))
+    return planes

@@ -226,3 +226,48 @@ def test_upsample_align_corners():
     out = ops.upsample_align_corners(x, 448, 448)
     ref = F.interpolate(x, size=(448, 448), mode="bilinear", align_corners=True)
     assert (out - ref).abs().max().item() < 1e-5
+
+
+def test_prompt_rasteriser_bitexact_vs_cv2():
+    """csrc/raster.cu against cv2.rectangle / cv2.polylines (thickness 3) -- the calls of reference is_model.py:109,129 -- for
+    vertices anywhere inside the image: long and short segments, repeated points, image corners and borders."""
+    import cv2
+    from pvpuformer_b200 import ops
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    for size in (448, 97):
+        # boxes: random corners, degenerate (zero) boxes, boxes touching the border
+        B = 64
+        xc, yc = rng.integers(0, size, B), rng.integers(0, size, B)
+        w = np.minimum(rng.integers(0, size, B), 2 * np.minimum(xc, size - 1 - xc))
+        h = np.minimum(rng.integers(0, size, B), 2 * np.minimum(yc, size - 1 - yc))
+        boxes = np.stack([xc, yc, w, h, rng.integers(0, 8, B)], axis=1).astype(np.int32)
+        boxes[0] = 0
+        boxes[1] = [size // 2, size // 2, size - 1 - (size - 1) % 2, size - 1 - (size - 1) % 2, 5]
+        n = 4
+        got = ops.raster_prompts(1, torch.from_numpy(boxes).to(dev), None, n, B, size).cpu().numpy()
+        for b in range(B):
+            ref = np.zeros((2, size, size), np.uint8)
+            x0, x1 = int(boxes[b, 0] - boxes[b, 2] // 2), int(boxes[b, 0] + boxes[b, 2] // 2)
+            y0, y1 = int(boxes[b, 1] - boxes[b, 3] // 2), int(boxes[b, 1] + boxes[b, 3] // 2)
+            cv2.rectangle(ref[0 if boxes[b, 4] < n else 1], (x0, y0), (x1, y1), 1, 3)
+            assert np.array_equal(got[b], ref), (size, b, boxes[b], int((got[b] != ref).sum()))
+        # polylines: smooth curves sampled densely (the reference's 1000-point scribbles), random walks, far-apart points
+        B, S = 24, 200
+        curves = np.zeros((B, S, 2), np.int32)
+        t = np.linspace(0, 1, S)
+        for b in range(B):
+            if b % 3 == 0:
+                c = rng.uniform(0, size - 1, (4, 2))
+                pts = ((1 - t)[:, None] ** 3 * c[0] + 3 * ((1 - t) ** 2 * t)[:, None] * c[1] + 3 * ((1 - t) * t ** 2)[:, None] * c[2] + (t ** 3)[:, None] * c[3])
+            elif b % 3 == 1:
+                pts = np.cumsum(rng.integers(-3, 4, (S, 2)), axis=0) + size // 2
+            else:
+                pts = rng.uniform(0, size - 1, (S, 2))
+            curves[b] = np.clip(pts, 0, size - 1).astype(np.int32)
+        curves[3, :, :] = curves[3, :1, :]                       # one point repeated: circles only
+        got = ops.raster_prompts(2, None, torch.from_numpy(curves).to(dev), 4, B, size).cpu().numpy()
+        for b in range(B):
+            ref = np.zeros((2, size, size), np.uint8)
+            cv2.polylines(ref[0], [curves[b]], False, 1, 3)
+            assert np.array_equal(got[b], ref), (size, b, int((got[b] != ref).sum()))
