@@ -17,6 +17,7 @@ class SyntheticEllipseDataset:
     def __init__(self, num_images=1024, size=448, seed0=0):
         self.num_images, self.size, self.seed0 = num_images, size, seed0
         self.name = "SyntheticEllipses"
+        self._grid = np.mgrid[0:size, 0:size]
 
     def __len__(self):
         return self.num_images
@@ -26,6 +27,6 @@ class SyntheticEllipseDataset:
         image = (rs.rand(self.size, self.size, 3) * 255).astype(np.uint8)
         cy, cx = rs.uniform(100, self.size - 100, 2)
         a, b = rs.uniform(40, 140, 2)
-        yy, xx = np.mgrid[0:self.size, 0:self.size]
+        yy, xx = self._grid
         mask = ((((yy - cy) / a) ** 2 + ((xx - cx) / b) ** 2) <= 1).astype(np.int32)
         return Sample(image, mask)
