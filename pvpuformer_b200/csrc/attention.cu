@@ -51,6 +51,14 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// one MUFU.EX2: the arguments are <= 0 (or -inf for masked keys), results in [0, 1]; exp2f() costs five instructions per element
+// for its denormal range handling, which this softmax never needs
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a) {
     pdl_launch_dependents();
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float mnew = fmaxf(mrow[r], mx[r]);   // finite: every tile has >= 1 valid key
-            corr[r] = exp2f(mrow[r] - mnew);
+            corr[r] = ex2_fast(mrow[r] - mnew);
             mrow[r] = mnew;
             lrow[r] *= corr[r];
         }
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         for (int nt = 0; nt < ATT_BN / 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float p = exp2f(s[nt][e] - mrow[e >> 1]);
+                const float p = ex2_fast(s[nt][e] - mrow[e >> 1]);
                 s[nt][e] = p;
                 psum[e >> 1] += p;
             }
