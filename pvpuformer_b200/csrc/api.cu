@@ -318,6 +318,7 @@ int fill_ppue_args(const vpu_context& h, const vpu_prompts& pr, PpueArgs& a) {
 
 int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int B, float* instances, float* aux,
                 uint8_t* ws, cudaStream_t s) {
+    pdl_set_auto((size_t)B * h.N() <= 16384);     // small batches are launch-latency-bound (B=2: -16 %, 8: -9 %, 16: -4 %): see pdl_enabled()
     Fwd f{h, s, ws, make_plan(h, B), B};
     const int C = h.C(), N = h.N(), M = B * N, Q = h.Q(), MQ = B * Q, g = h.grid(), img = h.d.img_size;
     const int heads = h.d.num_heads, hd = C / heads;

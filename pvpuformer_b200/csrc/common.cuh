@@ -29,7 +29,8 @@ unsigned long long launch_count();
         }                                 \
     } while (0)
 
-bool pdl_enabled();      // VPU_PDL=1 switches the launch attribute on (off by default, see gemm.cu)
+bool pdl_enabled();      // programmatic dependent launch: VPU_PDL=1/0 forces it, default = the forward's choice (gemm.cu)
+void pdl_set_auto(bool on);   // per-thread default used when VPU_PDL is not set (run_forward: on for small batches)
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -30,11 +30,15 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+// Programmatic dependent launch.  VPU_PDL=1 / 0 forces it on / off; by default the forward switches it on for small batches only
+// (pdl_set_auto): a batch-2 forward (one NoBRS click with flip TTA) is a chain of ~180 launch-latency-bound kernels and gains
+// 16 % (2.38 -> 2.00 ms), while on the batch-64 step of the power-capped B200s of this pool closing the inter-kernel gaps lowered
+// the SM clock by as much as it saved (16.54 ms at 1620 MHz with PDL, 16.15 ms at 1725 MHz without).
+static thread_local bool g_pdl_auto = false;
+void pdl_set_auto(bool on) { g_pdl_auto = on; }
 bool pdl_enabled() {
-    // off by default: on the power-capped (~400 W) B200s of this pool closing the inter-kernel gaps lowered the SM clock
-    // by as much as it saved (A/B, batch-64 ViT-B step: 16.54 ms at 1620 MHz with PDL, 16.15 ms at 1725 MHz without)
-    static const bool on = [] { const char* e = getenv("VPU_PDL"); return e && e[0] == '1'; }();
-    return on;
+    static const int forced = [] { const char* e = getenv("VPU_PDL"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    return forced >= 0 ? forced == 1 : g_pdl_auto;
 }
 
 static std::atomic<unsigned long long> g_launches{0};
