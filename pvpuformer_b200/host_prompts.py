@@ -4,10 +4,10 @@
   with Python's global `random` (reference isegm/model/ops.py:271-295), so reproducing its output
   for a given `random.seed` means consuming `random.randint` in exactly its order on the host.
   Only the integer selection happens here; the Gaussian values are evaluated on the device.
-* box / scribble rasterisation into the click planes for prompts with vertices OUTSIDE the image: one
-  `cv2.rectangle` / `cv2.polylines` (thickness 3) per sample, exactly the calls of reference
-  isegm/model/is_model.py:97-146.  Prompts inside the image (everything the reference's simulators produce)
-  are rasterised on the device by csrc/raster.cu, which restates OpenCV's fixed-point thick-line fill bit for bit.
+* `raster_planes`: the reference's `cv2.rectangle` / `cv2.polylines` calls (isegm/model/is_model.py:97-146), kept as the
+  checker of the device rasteriser (csrc/raster.cu) in tests and tools; the forward does not call it.  Prompts with a
+  vertex outside the image -- which the reference's simulators never produce and which cv2 clips its own way -- are
+  refused by the forward (`box_corners_inside`).
 """
 import random
 

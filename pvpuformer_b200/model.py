@@ -202,16 +202,15 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
             pr.ppue_points = pp.data_ptr()
             pr.n_ppue = pp.shape[1] // 2
             size = self.cfg.img_size
-            em = None
             if as_prompt_type == 1:
                 bx = boxes.to(device=device, dtype=torch.int32).contiguous()
                 keep.append(bx)
                 pr.boxes = bx.data_ptr()
                 boxes_np = boxes.detach().cpu().numpy()
-                if host_prompts.box_corners_inside(boxes_np, size):        # device rasteriser (csrc/raster.cu): bit-exact with cv2 there
-                    em = ops.raster_prompts(1, bx, None, n, B, size)
-                else:
-                    planes = host_prompts.raster_planes(1, boxes_np, None, n, B, size)
+                if not host_prompts.box_corners_inside(boxes_np, size):
+                    raise L.VpuError("box prompt with a corner outside the %d x %d image: the device rasteriser (csrc/raster.cu) is "
+                                     "bit-exact with cv2.rectangle only inside the image, and there is no host fallback" % (size, size))
+                em = ops.raster_prompts(1, bx, None, n, B, size)
             else:
                 sel = np.stack([host_prompts.scribble_select(np.asarray(scribbles)[b][0], np.asarray(rects)[b][0],
                                                              self.cfg.img_size, random) for b in range(B)])
@@ -222,14 +221,12 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
                 pr.scrib_sel = sel_t.data_ptr()
                 pr.scrib_slot = slot_t.data_ptr()
                 curve = np.stack([np.asarray(scribbles[b][0])[:, :2] for b in range(B)]).astype(np.int32)     # is_model.py:128 (x, y)
-                if curve.min() >= 0 and curve.max() < size:
-                    cv = torch.from_numpy(curve).to(device)
-                    keep.append(cv)
-                    em = ops.raster_prompts(2, None, cv, n, B, size)
-                else:
-                    planes = host_prompts.raster_planes(2, None, scribbles, n, B, size)
-            if em is None:          # vertices outside the image: the reference's own host call (cv2 clips those lines its own way)
-                em = torch.from_numpy(planes).to(device)
+                if curve.min() < 0 or curve.max() >= size:
+                    raise L.VpuError("scribble prompt with a point outside the %d x %d image: the device rasteriser (csrc/raster.cu) is "
+                                     "bit-exact with cv2.polylines only inside the image, and there is no host fallback" % (size, size))
+                cv = torch.from_numpy(curve).to(device)
+                keep.append(cv)
+                em = ops.raster_prompts(2, None, cv, n, B, size)
             keep.append(em)
             pr.extra_mask = em.data_ptr()
         return pr

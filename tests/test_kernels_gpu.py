@@ -232,7 +232,7 @@ def test_prompt_rasteriser_bitexact_vs_cv2():
     """csrc/raster.cu against cv2.rectangle / cv2.polylines (thickness 3) -- the calls of reference is_model.py:109,129 -- for
     vertices anywhere inside the image: long and short segments, repeated points, image corners and borders."""
     import cv2
-    from pvpuformer_b200 import ops
+    from pvpuformer_b200 import host_prompts, ops
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(5)
     for size in (448, 97):
@@ -246,12 +246,9 @@ def test_prompt_rasteriser_bitexact_vs_cv2():
         boxes[1] = [size // 2, size // 2, size - 1 - (size - 1) % 2, size - 1 - (size - 1) % 2, 5]
         n = 4
         got = ops.raster_prompts(1, torch.from_numpy(boxes).to(dev), None, n, B, size).cpu().numpy()
+        want = host_prompts.raster_planes(1, boxes, None, n, B, size)            # the reference's cv2.rectangle calls
         for b in range(B):
-            ref = np.zeros((2, size, size), np.uint8)
-            x0, x1 = int(boxes[b, 0] - boxes[b, 2] // 2), int(boxes[b, 0] + boxes[b, 2] // 2)
-            y0, y1 = int(boxes[b, 1] - boxes[b, 3] // 2), int(boxes[b, 1] + boxes[b, 3] // 2)
-            cv2.rectangle(ref[0 if boxes[b, 4] < n else 1], (x0, y0), (x1, y1), 1, 3)
-            assert np.array_equal(got[b], ref), (size, b, boxes[b], int((got[b] != ref).sum()))
+            assert np.array_equal(got[b], want[b]), (size, b, boxes[b], int((got[b] != want[b]).sum()))
         # polylines: smooth curves sampled densely (the reference's 1000-point scribbles), random walks, far-apart points
         B, S = 24, 200
         curves = np.zeros((B, S, 2), np.int32)
