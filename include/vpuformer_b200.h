@@ -131,8 +131,8 @@ int vpu_noc_next_clicks(const int8_t* gt, const uint8_t* pred, uint8_t* not_clic
                         int64_t* iou_counts, void* workspace /* 256-byte aligned */, size_t workspace_bytes, void* stream);
 /* Box / scribble outline planes on the device: replaces the host calls
  * cv2.rectangle(img, (x0,y0), (x1,y1), 255, 3) of draw_box and cv2.polylines(img, [curve], False, 255, 3) of draw_scribble
- * (isegm/model/is_model.py:97-146).  Bit-exact with OpenCV's fixed-point thick-line fill for vertices inside the image
- * (what the reference's prompt simulators produce); the result is the `extra_mask` operand of vpu_prompts.
+ * (isegm/model/is_model.py:97-146).  Bit-exact with OpenCV's fixed-point thick-line fill (vertices inside or outside the
+ * image); the result is the `extra_mask` operand of vpu_prompts.
  *   type 1: boxes int32 [B,5] (x_c, y_c, w, h, slot) -> outline in plane 0 if slot < n else plane 1
  *   type 2: scribbles int32 [B,S,2] (x, y) -> open polyline in plane 0
  *   planes uint8 [B,2,size,size], cleared by the call */

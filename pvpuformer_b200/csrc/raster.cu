@@ -1,6 +1,6 @@
 // Box / scribble prompt rasteriser: the 3-pixel outline the reference draws into the click planes
 // with cv2.rectangle(img, (x0, y0), (x1, y1), 255, 3) and cv2.polylines(img, [curve], False, 255, 3)
-// (isegm/model/is_model.py:97-146), bit-exact for vertices inside the image.
+// (isegm/model/is_model.py:97-146), bit-exact for vertices anywhere (inside or outside the image).
 //
 // The arithmetic is OpenCV's (modules/imgproc/src/drawing.cpp, 4.x; the reference pins opencv-python 4.7.0.68, this image has
 // 4.13 -- same code path): a thick line of thickness t between integer points is
@@ -12,8 +12,7 @@
 //     first segment of an open polyline.
 // cv2.rectangle = closed polyline through (x0,y0) (x1,y0) (x1,y1) (x0,y1); a zero-length segment draws only its circle(s).
 // One thread rasterises one segment; all threads store the same value, so overlapping stores need no ordering.
-// Validated against cv2 in tests/test_kernels_gpu.py for vertices inside the image (the prompts the reference builds never
-// leave it); the host wrapper keeps the cv2 call for anything else.
+// Validated against cv2 in tests/test_kernels_gpu.py (vertices inside the image, on its border and up to 60 px outside).
 #include "raster.cuh"
 
 namespace vpu {
@@ -191,8 +190,17 @@ __device__ void fill_circle(const Plane& im, int cx, int cy, int radius) {
     }
 }
 
-// ThickLine for integer end points (shift 0), thickness > 1, line_type 8; flags: 1 = cap at p0, 2 = cap at p1
+// ThickLine for integer end points (shift 0), thickness > 1, line_type 8; flags: 1 = cap at p0, 2 = cap at p1.
+// The segment is first clipped (integer Cohen-Sutherland) to the image rectangle grown by `thickness` pixels on every side --
+// measured against cv2 4.13: segments are reproduced bit for bit for end points anywhere with exactly this margin, and only
+// with it -- and the quadrilateral and the caps are built on the clipped end points; a segment outside that rectangle draws
+// nothing.
 __device__ void thick_line(const Plane& im, int ax, int ay, int bx, int by, int thickness, int flags) {
+    {
+        i64 x1 = (i64)ax + thickness, y1 = (i64)ay + thickness, x2 = (i64)bx + thickness, y2 = (i64)by + thickness;
+        if (!clip_line((i64)im.W + 2 * thickness, (i64)im.H + 2 * thickness, x1, y1, x2, y2)) return;
+        ax = (int)x1 - thickness; ay = (int)y1 - thickness; bx = (int)x2 - thickness; by = (int)y2 - thickness;
+    }
     i64 p0x = (i64)ax << XY_SHIFT, p0y = (i64)ay << XY_SHIFT;
     const i64 p1x = (i64)bx << XY_SHIFT, p1y = (i64)by << XY_SHIFT;
     const double inv = 1.0 / (double)XY_ONE;

@@ -5,9 +5,7 @@
   for a given `random.seed` means consuming `random.randint` in exactly its order on the host.
   Only the integer selection happens here; the Gaussian values are evaluated on the device.
 * `raster_planes`: the reference's `cv2.rectangle` / `cv2.polylines` calls (isegm/model/is_model.py:97-146), kept as the
-  checker of the device rasteriser (csrc/raster.cu) in tests and tools; the forward does not call it.  Prompts with a
-  vertex outside the image -- which the reference's simulators never produce and which cv2 clips its own way -- are
-  refused by the forward (`box_corners_inside`).
+  checker of the device rasteriser (csrc/raster.cu) in tests; the forward does not call it.
 """
 import random
 
@@ -49,14 +47,6 @@ def scribble_slots(ppue_points_cpu, n):
         if len(valid):
             out[b] = valid[-1]
     return out
-
-
-def box_corners_inside(boxes_cpu, size=448):
-    """True if every box outline has its four corners inside the image (then csrc/raster.cu reproduces cv2.rectangle exactly)."""
-    b = np.asarray(boxes_cpu).astype(np.int64)
-    x0, x1 = b[:, 0] - b[:, 2] // 2, b[:, 0] + b[:, 2] // 2
-    y0, y1 = b[:, 1] - b[:, 3] // 2, b[:, 1] + b[:, 3] // 2
-    return bool(min(x0.min(), x1.min(), y0.min(), y1.min()) >= 0 and max(x0.max(), x1.max(), y0.max(), y1.max()) < size)
 
 
 def raster_planes(as_prompt_type, boxes_cpu, scribbles, n, B, size=448):

@@ -206,11 +206,7 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
                 bx = boxes.to(device=device, dtype=torch.int32).contiguous()
                 keep.append(bx)
                 pr.boxes = bx.data_ptr()
-                boxes_np = boxes.detach().cpu().numpy()
-                if not host_prompts.box_corners_inside(boxes_np, size):
-                    raise L.VpuError("box prompt with a corner outside the %d x %d image: the device rasteriser (csrc/raster.cu) is "
-                                     "bit-exact with cv2.rectangle only inside the image, and there is no host fallback" % (size, size))
-                em = ops.raster_prompts(1, bx, None, n, B, size)
+                em = ops.raster_prompts(1, bx, None, n, B, size)        # cv2.rectangle(..., 3) of draw_box, on the device
             else:
                 sel = np.stack([host_prompts.scribble_select(np.asarray(scribbles)[b][0], np.asarray(rects)[b][0],
                                                              self.cfg.img_size, random) for b in range(B)])
@@ -221,10 +217,7 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
                 pr.scrib_sel = sel_t.data_ptr()
                 pr.scrib_slot = slot_t.data_ptr()
                 curve = np.stack([np.asarray(scribbles[b][0])[:, :2] for b in range(B)]).astype(np.int32)     # is_model.py:128 (x, y)
-                if curve.min() < 0 or curve.max() >= size:
-                    raise L.VpuError("scribble prompt with a point outside the %d x %d image: the device rasteriser (csrc/raster.cu) is "
-                                     "bit-exact with cv2.polylines only inside the image, and there is no host fallback" % (size, size))
-                cv = torch.from_numpy(curve).to(device)
+                cv = torch.from_numpy(curve).to(device)                   # cv2.polylines(..., 3) of draw_scribble, on the device
                 keep.append(cv)
                 em = ops.raster_prompts(2, None, cv, n, B, size)
             keep.append(em)

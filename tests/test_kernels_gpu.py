@@ -230,7 +230,7 @@ def test_upsample_align_corners():
 
 def test_prompt_rasteriser_bitexact_vs_cv2():
     """csrc/raster.cu against cv2.rectangle / cv2.polylines (thickness 3) -- the calls of reference is_model.py:109,129 -- for
-    vertices anywhere inside the image: long and short segments, repeated points, image corners and borders."""
+    vertices inside the image (long and short segments, repeated points, corners, borders) and outside it."""
     import cv2
     from pvpuformer_b200 import host_prompts, ops
     dev = torch.device("cuda:0")
@@ -249,6 +249,18 @@ def test_prompt_rasteriser_bitexact_vs_cv2():
         want = host_prompts.raster_planes(1, boxes, None, n, B, size)            # the reference's cv2.rectangle calls
         for b in range(B):
             assert np.array_equal(got[b], want[b]), (size, b, boxes[b], int((got[b] != want[b]).sum()))
+        # boxes and curves that leave the image (cv2 clips each segment to the image grown by the thickness first)
+        far = np.stack([rng.integers(-60, size + 60, B), rng.integers(-60, size + 60, B), rng.integers(0, 2 * size, B),
+                        rng.integers(0, 2 * size, B), rng.integers(0, 8, B)], axis=1).astype(np.int32)
+        got = ops.raster_prompts(1, torch.from_numpy(far).to(dev), None, n, B, size).cpu().numpy()
+        want = host_prompts.raster_planes(1, far, None, n, B, size)
+        assert np.array_equal(got, want), (size, int((got != want).sum()))
+        wild = rng.integers(-60, size + 60, (B, 40, 2)).astype(np.int32)
+        got = ops.raster_prompts(2, None, torch.from_numpy(wild).to(dev), n, B, size).cpu().numpy()
+        for b in range(B):
+            ref = np.zeros((2, size, size), np.uint8)
+            cv2.polylines(ref[0], [wild[b]], False, 1, 3)
+            assert np.array_equal(got[b], ref), (size, b, int((got[b] != ref).sum()))
         # polylines: smooth curves sampled densely (the reference's 1000-point scribbles), random walks, far-apart points
         B, S = 24, 200
         curves = np.zeros((B, S, 2), np.int32)
