@@ -96,7 +96,7 @@ def noc_next_clicks(gt, pred, not_clicked, workspace=None):
 
 def raster_prompts(as_prompt_type, boxes, scribbles, n, B, size=448, device=None):
     """Box / scribble outline planes uint8 [B,2,size,size] (csrc/raster.cu; reference is_model.py:97-146 through cv2).
-    boxes: int32 cuda [B,5]; scribbles: int32 cuda [B,S,2] (x, y).  Vertices must lie inside the image (checked by the caller)."""
+    boxes: int32 cuda [B,5]; scribbles: int32 cuda [B,S,2] (x, y); vertices may lie outside the image (clipped as cv2 does)."""
     dev = device or (boxes.device if as_prompt_type == 1 else scribbles.device)
     planes = torch.empty(B, 2, size, size, dtype=torch.uint8, device=dev)
     S = 0 if as_prompt_type == 1 else scribbles.shape[1]
