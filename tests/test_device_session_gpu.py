@@ -148,3 +148,45 @@ def test_device_sessions_refuse_what_they_cannot_do():
         DeviceClickSessions([a[0], b[0]], [a[1], b[1]], dev)
     with pytest.raises(ValueError):
         DeviceClickSessions([a[0]], [a[1]], dev, max_clicks=30)
+
+
+def test_session_kernels_on_large_non_square_images_and_ignore_labels():
+    """1000 x 1400 images (ZoomIn crops are real down-scales there), ground truth with ignore labels: the device sessions track
+    the host predictors for a few clicks."""
+    from pvpuformer_b200.inference.device_session import DeviceClickSessions
+    dev = torch.device("cuda:0")
+    net = BlobNet().to(dev)
+    samples = _samples(2, 1000, 1400, seed=77)
+    rng = np.random.default_rng(3)
+    samples = [(im, np.where(rng.random(gt.shape) < 0.02, -1, gt).astype(np.int32)) for im, gt in samples]
+    S, K = len(samples), 4
+    eng = DeviceClickSessions([s[0] for s in samples], [s[1] for s in samples], dev, max_clicks=K)
+    hosts = [vpu_eval_predictor(net, dev) for _ in samples]
+    clickers = [Clicker(gt_mask=s[1]) for s in samples]
+    masks = [np.zeros(s[1].shape, bool) for s in samples]
+    for p, s in zip(hosts, samples):
+        p.set_input_image(s[0])
+    eng.clicker_step(0)
+    with torch.no_grad():
+        for k in range(K):
+            image, points = eng.prepare()
+            roi = eng.roi.cpu().numpy()
+            logits_h = []
+            for s in range(S):
+                clickers[s].make_next_click(masks[s])
+                image_nd, points_nd, _ = hosts[s].prepare_inputs(clickers[s], None, samples[s][1], 0)
+                assert tuple(roi[s]) == tuple(int(v) for v in hosts[s].zoom_in._object_roi), (k, s)
+                assert torch.equal(torch.stack([points[s], points[S + s]]), _repack_points(points_nd.to(torch.float64), eng.n_half))
+                assert (torch.stack([image[s], image[S + s]]) - image_nd).abs().max().item() <= 2e-6
+                logits_h.append(net(image_nd, points_nd)["instances"])
+            eng.finish(net(image, points)["instances"])
+            eng.clicker_step(k + 1)
+            ious = eng.ious(k + 1)
+            for s in range(S):
+                full = hosts[s].finish_prediction(logits_h[s], (T, T))
+                hosts[s].prev_prediction = full
+                assert (eng.prev_probs[s] - full[0, 0]).abs().max().item() <= 2e-6
+                dm = eng.pred[s].cpu().numpy().astype(bool)
+                assert (dm != (full.cpu().numpy()[0, 0] > 0.49)).sum() <= 4
+                masks[s] = dm
+                assert abs(ious[s] - get_iou(samples[s][1], dm)) <= 1e-12
