@@ -17,6 +17,7 @@ namespace vpu {
 constexpr int ATT_BM = 64;   // query rows per CTA
 constexpr int ATT_BN = 64;   // keys per tile
 constexpr int ATT_THREADS = 128;
+constexpr int ATT_KROW_MAX = 256;   // keys of one window (16 x 16 for ViT-H)
 
 __device__ __forceinline__ int map_row(const RowMap& rm, int prob, int s) {
     if (rm.mode == 0) return prob * rm.per_prob + s;
@@ -84,12 +85,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         const size_t row = ok ? (size_t)map_row(a.qmap, prob, s) : 0;
         cp_async16(Qs + r * PITCH + c * 8, qbase + row * a.ldq + c * 8, ok);
     }
+    // window regrouping of the keys (map_row: six integer divisions) worked out once per CTA instead of once per 16-byte
+    // chunk of every tile: the divisions were ~40 % of the kernel's instructions on the ViT-H windows (ncu, round 1h)
+    __shared__ int krow[ATT_KROW_MAX];
+    const bool ktab = a.kmap.mode == 1 && a.Sk <= ATT_KROW_MAX;
+    if (ktab) {
+        for (int s = tid; s < a.Sk; s += ATT_THREADS) krow[s] = map_row(a.kmap, prob, s);
+        __syncthreads();
+    }
     auto load_kv = [&](int tile, int buf) {
         for (int idx = tid; idx < ATT_BN * CHUNKS; idx += ATT_THREADS) {
             const int r = idx / CHUNKS, c = idx % CHUNKS;
             const int s = tile * ATT_BN + r;
             const bool ok = s < a.Sk;
-            const size_t row = ok ? (size_t)map_row(a.kmap, prob, s) : 0;
+            const size_t row = ok ? (size_t)(ktab ? krow[s] : map_row(a.kmap, prob, s)) : 0;
             cp_async16(Ks + (buf * ATT_BN + r) * PITCH + c * 8, kbase + row * a.ldk + c * 8, ok);
             cp_async16(Vs + (buf * ATT_BN + r) * PITCH + c * 8, vbase + row * a.ldv + c * 8, ok);
         }
@@ -136,25 +145,28 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
             }
         }
         // ---- mask + online softmax (rows g and g+8 of this warp's 16) ------------------------
+        // raw scores: the positive scale commutes with the maximum and is applied inside the exponent's FMA
         const int kbase_idx = tile * ATT_BN;
+        if (kbase_idx + ATT_BN > a.Sk) {                 // ragged last tile only
+#pragma unroll
+            for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (kbase_idx + nt * 8 + 2 * t + (e & 1) >= a.Sk) s[nt][e] = -INFINITY;
+            }
+        }
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int nt = 0; nt < ATT_BN / 8; ++nt) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = kbase_idx + nt * 8 + 2 * t + (e & 1);
-                float v = s[nt][e] * sl2;
-                if (key >= a.Sk) v = -INFINITY;
-                s[nt][e] = v;
-                mx[e >> 1] = fmaxf(mx[e >> 1], v);
-            }
+            for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
         }
         float corr[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-            const float mnew = fmaxf(mrow[r], mx[r]);   // finite: every tile has >= 1 valid key
+            const float mnew = fmaxf(mrow[r], mx[r] * sl2);   // finite: every tile has >= 1 valid key
             corr[r] = ex2_fast(mrow[r] - mnew);
             mrow[r] = mnew;
             lrow[r] *= corr[r];
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         for (int nt = 0; nt < ATT_BN / 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float p = ex2_fast(s[nt][e] - mrow[e >> 1]);
+                const float p = ex2_fast(fmaf(s[nt][e], sl2, -mrow[e >> 1]));
                 s[nt][e] = p;
                 psum[e >> 1] += p;
             }
