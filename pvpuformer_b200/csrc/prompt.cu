@@ -114,28 +114,35 @@ int ppue_launch(const PpueArgs& a, int B, cudaStream_t stream) {
 // to fp32 (what torch's in-place add_ on a float32 grid does with float64 clicks).
 // ------------------------------------------------------------------------------------------
 struct SmemPoints {
-    double pr[2 * 24], pc[2 * 24];
+    double pc[2 * 24];      // column of the clicks that can reach this image row
+    float dr2[2 * 24];      // fl32(fl32(r - pr)^2) of the same clicks
     int cnt[2];
 };
 
-__device__ __forceinline__ void load_points(SmemPoints& sp, const double* pts, int n) {
-    // compact the valid points of each half so the per-pixel loop only visits real clicks
+// A CTA works on one image row r: only clicks with fl32(r - pr)^2 <= R^2 can produce d <= R^2 on it (the second term is
+// non-negative and fp32 addition is monotone), so each half's valid clicks are filtered once per CTA -- typically 0 or 1 of up
+// to 24 survive -- and the row term is computed once.  The per-pixel loop used to evaluate two double-precision differences per
+// click and pixel (the reference's arithmetic: difference in double, rounded once to fp32); the column difference still is.
+__device__ __forceinline__ void load_points(SmemPoints& sp, const double* pts, int n, int r, float r2) {
     if (threadIdx.x < 2) {
         const int h = threadIdx.x;
         int k = 0;
         for (int i = 0; i < n; ++i) {
             const double* p = pts + (size_t)(h * n + i) * 3;
-            if (fmax(p[0], p[1]) >= 0.0) { sp.pr[h * 24 + k] = p[0]; sp.pc[h * 24 + k] = p[1]; ++k; }
+            if (fmax(p[0], p[1]) >= 0.0) {
+                const float dr = (float)((double)r - p[0]);
+                const float d2 = __fmul_rn(dr, dr);
+                if (d2 <= r2) { sp.pc[h * 24 + k] = p[1]; sp.dr2[h * 24 + k] = d2; ++k; }
+            }
         }
         sp.cnt[h] = k;
     }
 }
-__device__ __forceinline__ bool disk_hit(const SmemPoints& sp, int h, int r, int c, float r2) {
+__device__ __forceinline__ bool disk_hit(const SmemPoints& sp, int h, int c, float r2) {
     bool hit = false;
     for (int k = 0; k < sp.cnt[h]; ++k) {
-        const float dr = (float)((double)r - sp.pr[h * 24 + k]);
         const float dc = (float)((double)c - sp.pc[h * 24 + k]);
-        const float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc));
+        const float d = __fadd_rn(sp.dr2[h * 24 + k], __fmul_rn(dc, dc));
         hit |= (d <= r2);
     }
     return hit;
@@ -147,16 +154,16 @@ __global__ void __launch_bounds__(256) coord_features_kernel(const CoordArgs a, 
     pdl_wait();
     __shared__ SmemPoints sp;
     const int y = blockIdx.x, b = blockIdx.y, H = a.H, W = a.W;
-    load_points(sp, a.points + (size_t)b * 2 * a.n * 3, a.n);
-    __syncthreads();
     const float r2 = a.radius * a.radius;
+    load_points(sp, a.points + (size_t)b * 2 * a.n * 3, a.n, y, r2);
+    __syncthreads();
     const float* prev = a.image4 + (((size_t)b * 4 + 3) * H + y) * W;
     float* o = out + ((size_t)b * 3 * H + y) * W;
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
         o[x] = prev[x];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            bool hit = disk_hit(sp, h, y, x, r2);
+            bool hit = disk_hit(sp, h, x, r2);
             if (a.extra_mask) hit |= a.extra_mask[(((size_t)b * 2 + h) * H + y) * W + x] != 0;
             o[(size_t)(h + 1) * H * W + x] = hit ? 1.f : 0.f;
         }
@@ -182,9 +189,9 @@ __global__ void __launch_bounds__(256) patch_operand_kernel(const CoordArgs a, _
     pdl_wait();
     __shared__ SmemPoints sp;
     const int y = blockIdx.x, b = blockIdx.y, H = a.H, W = a.W;
-    load_points(sp, a.points + (size_t)b * 2 * a.n * 3, a.n);
-    __syncthreads();
     const float r2 = a.radius * a.radius;
+    load_points(sp, a.points + (size_t)b * 2 * a.n * 3, a.n, y, r2);
+    __syncthreads();
     const int g = W / p, gy = y / p, ph = y % p, pp = p * p;
     for (int x = 2 * threadIdx.x; x < W; x += 2 * blockDim.x) {
         const int gx = x / p, pw = x % p;
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(256) patch_operand_kernel(const CoordArgs a, _
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            bool h0 = disk_hit(sp, h, y, x, r2), h1 = disk_hit(sp, h, y, x + 1, r2);
+            bool h0 = disk_hit(sp, h, x, r2), h1 = disk_hit(sp, h, x + 1, r2);
             if (a.extra_mask) {
                 const uint8_t* em = a.extra_mask + (((size_t)b * 2 + h) * H + y) * W + x;
                 h0 |= em[0] != 0;
