@@ -192,6 +192,29 @@ def test_forward_vs_oracle_fresh_inputs_and_batch_independence():
         m.want_aux = True
 
 
+def test_full_size_batch_properties_config2():
+    """BASELINE.json configs[1] at full size (batch 64, 1..20 clicks per image, the bench workload): the forward is
+    deterministic, every checked sample equals its own batch-1 forward bit for bit (which also crosses the small-batch
+    programmatic-dependent-launch mode), and two samples are checked against the CPU oracle."""
+    from pvpuformer_b200.synthetic import workload
+    m, sd = _model("vit_base")
+    image4, pts = workload("vit_base", 64, seed=100)
+    img_d, pts_d = image4.cuda(), pts.cuda()
+    out = m(img_d, pts_d)
+    inst, aux = out["instances"].clone(), out["instances_aux"].clone()
+    again = m(img_d, pts_d)
+    assert torch.equal(again["instances"], inst) and torch.equal(again["instances_aux"], aux)
+    for i in (0, 17, 63):
+        solo = m(img_d[i:i + 1], pts_d[i:i + 1])
+        assert torch.equal(solo["instances"][0], inst[i]) and torch.equal(solo["instances_aux"][0], aux[i]), i
+    idx = [5, 40]
+    with torch.no_grad():
+        ref = vo.forward(sd, m.cfg, image4[idx], pts[idx])
+    assert (inst[idx].cpu() - ref["instances"]).abs().max().item() <= LOGIT_TOL
+    assert (aux[idx].cpu() - ref["instances_aux"]).abs().max().item() <= AUX_TOL
+    _rel_gates(inst[idx].cpu(), ref["instances"])
+
+
 def test_error_behaviour():
     from pvpuformer_b200 import lib as L
     m, _ = _model("vit_base")
