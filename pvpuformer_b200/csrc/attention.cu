@@ -255,6 +255,7 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
     VPU_REQUIRE(a.nprob <= 65535 && a.heads <= 65535, "attention grid too large");
     static const bool use_tc = [] { const char* e = getenv("VPU_ATTN_TC"); return !(e && e[0] == '0'); }();
     if (use_tc && window_attention_tc_supported(a, head_dim)) return window_attention_tc_launch(a, stream);
+    if (use_tc && window_attention_tc80_supported(a, head_dim)) return window_attention_tc80_launch(a, stream);
     if (use_tc && global_attention_tc_supported(a, head_dim)) return global_attention_tc_launch(a, stream);
     switch (head_dim) {
         case 48: return launch_att<48>(a, stream);

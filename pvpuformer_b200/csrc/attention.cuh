@@ -31,6 +31,9 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream);
 // tcgen05 / TMEM kernel for 14x14-token windows, head_dim 64 (attention_tc.cu)
 bool window_attention_tc_supported(const AttnArgs& a, int head_dim);
 int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
+// tcgen05 / TMEM kernel for 16x16-token windows, head_dim 80 (ViT-H; attention_tc.cu)
+bool window_attention_tc80_supported(const AttnArgs& a, int head_dim);
+int window_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream);
 // tcgen05 / TMEM flash kernel for un-windowed self-attention, head_dim 64, S a multiple of 112 (attention_tc.cu)
 bool global_attention_tc_supported(const AttnArgs& a, int head_dim);
 int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream);

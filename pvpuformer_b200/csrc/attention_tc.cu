@@ -744,6 +744,290 @@ global_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     }
 }
 
+// =====================================================================================================
+// ViT-H window attention: 16 x 16-token windows (256 queries = keys per problem), head_dim 80
+// (reference models_vit.py:43-56 per 224-px window with patch 14, models_vit.py:225-255, :317-319).
+//
+// Same dataflow as window_attention_tc_kernel (S and P live only in TMEM, O = P V with the A operand in TMEM), with
+// the two differences head_dim 80 forces:
+//   * 80 columns are not a swizzle span.  Every operand is staged as a 64-column part (128-byte swizzle) plus a
+//     16-column part (32-byte swizzle), each by its own TMA box; S = Q K^T takes four K = 16 steps on the main
+//     parts and a fifth on the tails, O = P V is an N = 64 and an N = 16 product per 16 keys (MN-major V parts).
+//   * a problem needs 120 KB of operands, so the ring is split: Q / K double-buffered (their last reader is the
+//     S product, issued one problem ahead), V single-buffered (reloaded as soon as the second P V product of the
+//     previous problem has completed; the softmax of the next problem covers the load).
+// Two full 128-query tiles per problem (8 window rows each) and 256 valid keys: no masking, no padded rows.
+// TMEM per tile (256 columns): S [0,256) fp32 -> P [0,128) bf16 in place -> O [128,192) + [192,208).
+// =====================================================================================================
+namespace h80 {
+constexpr int HD = 80, HM = 64, HT = 16;                 // head dim = main + tail columns
+constexpr int HWIN = 16, HSK = HWIN * HWIN, HQT = 128, HQ_IROWS = HQT / HWIN;
+constexpr int Q_MAIN = HQT * HM * 2, Q_TAIL = HQT * HT * 2, Q_TILE = Q_MAIN + Q_TAIL;       // 16 + 4 KB
+constexpr int KV_MAIN = HSK * HM * 2, KV_TAIL = HSK * HT * 2, KV_BUF = KV_MAIN + KV_TAIL;   // 32 + 8 KB
+constexpr int QK_STAGE = 2 * Q_TILE + KV_BUF;            // 80 KB: two Q tiles + K
+constexpr int V_OFF = 2 * QK_STAGE;
+constexpr int SMEM = V_OFF + KV_BUF + 1024;              // 201 KB
+constexpr int O_MAIN_COL = 128, O_TAIL_COL = 192;
+static_assert(Q_MAIN % 1024 == 0 && Q_TILE % 1024 == 0 && KV_MAIN % 1024 == 0 && KV_BUF % 1024 == 0, "swizzle atoms must stay aligned");
+}  // namespace h80
+
+// 32-byte-swizzled operand part (16 bf16 columns = one 32-byte row, 8-row atoms 256 B apart); the same bits describe the
+// K-major Q / K tails and the MN-major V tail (the major-ness lives in the instruction descriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmQt,
+                             const __grid_constant__ CUtensorMap tmKm, const __grid_constant__ CUtensorMap tmKt, const WinArgs a) {
+    using namespace h80;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t qk_full[2], qk_empty[2], v_full, v_empty, s_full[2], p_full[2], o_full[2], s_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQm);
+        tma_prefetch_desc(&tmQt);
+        tma_prefetch_desc(&tmKm);
+        tma_prefetch_desc(&tmKt);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&qk_full[s], 1);
+            mbar_init(&qk_empty[s], 1);
+            mbar_init(&s_full[s], 1);
+            mbar_init(&p_full[s], 4);
+            mbar_init(&o_full[s], 1);
+            mbar_init(&s_empty[s], 4);
+        }
+        mbar_init(&v_full, 1);
+        mbar_init(&v_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+    const int nw2 = a.nwin_side * a.nwin_side;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        int stage = 0;
+        uint32_t phase = 0, vph = 0;
+        for (int p = blockIdx.x; p < a.nprob; p += gridDim.x) {
+            const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
+            const int wi = w / a.nwin_side, wj = w % a.nwin_side, r0 = wi * HWIN;
+            const int qc = a.qcol + h * HD, kc = a.kcol + h * HD, vc = a.vcol + h * HD;
+            mbar_wait(&qk_empty[stage], phase ^ 1);
+            if (elect_one()) {
+                uint64_t* bar = &qk_full[stage];
+                mbar_arrive_expect_tx(bar, QK_STAGE);
+                uint8_t* st = smem + stage * QK_STAGE;
+                tma_load_5d(st, &tmQm, bar, qc, 0, wj, r0, b);
+                tma_load_5d(st + Q_MAIN, &tmQt, bar, qc + HM, 0, wj, r0, b);
+                tma_load_5d(st + Q_TILE, &tmQm, bar, qc, 0, wj, r0 + HQ_IROWS, b);
+                tma_load_5d(st + Q_TILE + Q_MAIN, &tmQt, bar, qc + HM, 0, wj, r0 + HQ_IROWS, b);
+                tma_load_5d(st + 2 * Q_TILE, &tmKm, bar, kc, 0, wj, r0, b);
+                tma_load_5d(st + 2 * Q_TILE + KV_MAIN, &tmKt, bar, kc + HM, 0, wj, r0, b);
+            }
+            __syncwarp();
+            mbar_wait(&v_empty, vph ^ 1);           // second P V product of the previous problem complete
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&v_full, KV_BUF);
+                tma_load_5d(smem + V_OFF, &tmKm, &v_full, vc, 0, wj, r0, b);
+                tma_load_5d(smem + V_OFF + KV_MAIN, &tmKt, &v_full, vc + HM, 0, wj, r0, b);
+            }
+            __syncwarp();
+            vph ^= 1;
+            if (++stage == 2) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (converged warp, one elected lane) ----------------
+        constexpr uint32_t idesc_s = idesc_bf16(128, HSK, false);
+        constexpr uint32_t idesc_om = idesc_bf16(128, HM, true), idesc_ot = idesc_bf16(128, HT, true);
+        const uint64_t qm0 = umma_desc_k_sw128(smem_base), qt0 = umma_desc_sw32(smem_base + Q_MAIN);
+        const uint64_t km0 = umma_desc_k_sw128(smem_base + 2 * Q_TILE), kt0 = umma_desc_sw32(smem_base + 2 * Q_TILE + KV_MAIN);
+        const uint64_t vm0 = umma_desc_mn_sw128(smem_base + V_OFF), vt0 = umma_desc_sw32(smem_base + V_OFF + KV_MAIN);
+        auto issue_s = [&](int t, int st, bool release_stage) {
+            if (elect_one()) {
+                const uint64_t so = (uint64_t)(st * (QK_STAGE >> 4)), to = so + (uint64_t)(t * (Q_TILE >> 4));
+                const uint32_t d = tmem_base + t * TILE_COLS;
+#pragma unroll
+                for (int k = 0; k < HM / 16; ++k) umma_bf16(d, qm0 + to + 2 * k, km0 + so + 2 * k, idesc_s, k ? 1u : 0u);
+                umma_bf16(d, qt0 + to, kt0 + so, idesc_s, 1u);
+                umma_commit(&s_full[t]);
+                if (release_stage) umma_commit(&qk_empty[st]);   // both S products of the stage have been issued
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int t, bool release_v) {
+            if (elect_one()) {
+                const uint32_t pt = tmem_base + t * TILE_COLS;
+#pragma unroll
+                for (int k = 0; k < HSK / 16; ++k) {     // 16 keys: 8 TMEM columns of P, 2048 B of the main and 512 B of the tail V part
+                    umma_bf16_ts(pt + O_MAIN_COL, pt + k * 8, vm0 + 128 * k, idesc_om, k ? 1u : 0u);
+                    umma_bf16_ts(pt + O_TAIL_COL, pt + k * 8, vt0 + 32 * k, idesc_ot, k ? 1u : 0u);
+                }
+                umma_commit(&o_full[t]);
+                if (release_v) umma_commit(&v_empty);
+            }
+            __syncwarp();
+        };
+        int stage = 0;
+        uint32_t phase = 0, tphase = 0;
+        int p = blockIdx.x;
+        if (p < a.nprob) {
+            mbar_wait(&qk_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0, false);
+            issue_s(1, 0, true);
+        }
+        for (; p < a.nprob; p += gridDim.x) {
+            const bool has_next = p + (int)gridDim.x < a.nprob;
+            const int nstage = stage ^ 1;
+            const uint32_t nphase = stage ? phase ^ 1 : phase;
+            mbar_wait(&p_full[0], tphase);
+            mbar_wait(&v_full, tphase);
+            tc_fence_after();
+            issue_pv(0, false);
+            if (has_next) {
+                mbar_wait(&qk_full[nstage], nphase);
+                mbar_wait(&s_empty[0], tphase);
+                tc_fence_after();
+                issue_s(0, nstage, false);
+            }
+            mbar_wait(&p_full[1], tphase);
+            tc_fence_after();
+            issue_pv(1, true);
+            if (has_next) {
+                mbar_wait(&s_empty[1], tphase);
+                tc_fence_after();
+                issue_s(1, nstage, true);
+            }
+            stage = nstage;
+            phase = nphase;
+            tphase ^= 1;
+        }
+    } else {  // ---------------- softmax + epilogue warpgroups ----------------
+        const int t = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t tile_tmem = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * TILE_COLS;
+        uint32_t tphase = 0;
+        for (int p = blockIdx.x; p < a.nprob; p += gridDim.x) {
+            const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
+            mbar_wait(&s_full[t], tphase);
+            tc_fence_after();
+            float sum0 = 0.f, sum1 = 0.f;
+            {
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32(tile_tmem, ra);
+#pragma unroll 1
+                for (int c = 0; c < 8; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tile_tmem + (c + 1) * 32, rb);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        mx0 = fmaxf(mx0, __uint_as_float(ra[i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(ra[i + 1]));
+                    }
+                    tmem_ld_wait();
+                    if (c + 2 < 8) tmem_ld_32x32(tile_tmem + (c + 2) * 32, ra);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        mx0 = fmaxf(mx0, __uint_as_float(rb[i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(rb[i + 1]));
+                    }
+                }
+                const float moff = fmaxf(mx0, mx1) * a.scale_log2;
+                auto expo = [&](uint32_t sbits) { return ex2_approx(fmaf(__uint_as_float(sbits), a.scale_log2, -moff)); };
+                tmem_ld_32x32(tile_tmem, ra);
+#pragma unroll 1
+                for (int c = 0; c < 8; c += 2) {
+                    uint32_t pk[16];
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tile_tmem + (c + 1) * 32, rb);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float p0 = expo(ra[2 * i]), p1 = expo(ra[2 * i + 1]);
+                        sum0 += p0; sum1 += p1;
+                        pk[i] = pack_bf16(p0, p1);
+                    }
+                    tmem_st_32x16(tile_tmem + c * 16, pk);
+                    tmem_ld_wait();
+                    if (c + 2 < 8) tmem_ld_32x32(tile_tmem + (c + 2) * 32, ra);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float p0 = expo(rb[2 * i]), p1 = expo(rb[2 * i + 1]);
+                        sum0 += p0; sum1 += p1;
+                        pk[i] = pack_bf16(p0, p1);
+                    }
+                    tmem_st_32x16(tile_tmem + (c + 1) * 16, pk);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t]);
+            // epilogue: O / rowsum -> bf16 -> token-major output row of this query (80 columns = ten 16-byte stores)
+            mbar_wait(&o_full[t], tphase);
+            tc_fence_after();
+            const float inv = 1.0f / (sum0 + sum1);
+            const int wi = w / a.nwin_side, wj = w % a.nwin_side;
+            const int s = t * HQT + row, i = s / HWIN, j = s % HWIN;
+            __nv_bfloat16* dst = a.o + ((size_t)b * a.tokens + (size_t)(wi * HWIN + i) * a.grid + wj * HWIN + j) * a.ldo + h * HD;
+            auto store8 = [&](__nv_bfloat16* d, const uint32_t* r) {
+                uint4 v;
+                v.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+                v.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+                v.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+                v.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+                *reinterpret_cast<uint4*>(d) = v;
+            };
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tile_tmem + O_MAIN_COL + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) store8(dst + c * 32 + q * 8, r + 8 * q);
+            }
+            {
+                uint32_t r[16];
+                tmem_ld_32x16(tile_tmem + O_TAIL_COL, r);
+                tmem_ld_wait();
+                store8(dst + HM, r);
+                store8(dst + HM + 8, r + 8);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[t]);
+            tphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---- host: 5-D tensor maps over the fused projection buffer --------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -780,31 +1064,34 @@ int init() {
     g_sms = prop.multiProcessorCount;
     VPU_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     VPU_CHECK_CUDA(cudaFuncSetAttribute(global_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h80::SMEM));
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
 
-// dims (innermost first): column, j inside the window, window column, grid row, image
-int make_map(CUtensorMap* tm, const void* ptr, int ld, int images, int grid, int irows) {
-    Key key{ptr, ld, images, grid, irows};
+// dims (innermost first): column, j inside the window, window column, grid row, image; box = cols x win x 1 x irows x 1
+int make_map_w(CUtensorMap* tm, const void* ptr, int ld, int images, int grid, int win, int irows, int cols, CUtensorMapSwizzle swz) {
+    Key key{ptr, ld, images, grid, irows | (cols << 8) | (win << 16) | ((int)swz << 24)};
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_cache.find(key);
         if (it != g_cache.end()) { *tm = it->second; return 0; }
     }
     const cuuint64_t row_b = (cuuint64_t)ld * 2;
-    cuuint64_t gdim[5] = {(cuuint64_t)ld, (cuuint64_t)WIN, (cuuint64_t)(grid / WIN), (cuuint64_t)grid, (cuuint64_t)images};
-    cuuint64_t gstride[4] = {row_b, WIN * row_b, (cuuint64_t)grid * row_b, (cuuint64_t)grid * grid * row_b};
-    cuuint32_t box[5] = {(cuuint32_t)D, (cuuint32_t)WIN, 1, (cuuint32_t)irows, 1};
+    cuuint64_t gdim[5] = {(cuuint64_t)ld, (cuuint64_t)win, (cuuint64_t)(grid / win), (cuuint64_t)grid, (cuuint64_t)images};
+    cuuint64_t gstride[4] = {row_b, win * row_b, (cuuint64_t)grid * row_b, (cuuint64_t)grid * grid * row_b};
+    cuuint32_t box[5] = {(cuuint32_t)cols, (cuuint32_t)win, 1, (cuuint32_t)irows, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VPU_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (5-D window map) failed with %d", (int)r);
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_cache.size() > 1024) g_cache.clear();
     g_cache[key] = *tm;
     return 0;
+}
+int make_map(CUtensorMap* tm, const void* ptr, int ld, int images, int grid, int irows) {
+    return make_map_w(tm, ptr, ld, images, grid, WIN, irows, D, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // plain 2-D map over a token-major [rows, ld] bf16 buffer: box = 64 columns x box_rows rows, 128B swizzle
@@ -885,6 +1172,33 @@ int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
     w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
     const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
     VPU_CHECK_CUDA(launch_pdl(window_attention_tc_kernel, dim3(ctas), dim3(THREADS), SMEM_BYTES, stream, tmKV, tmQ0, tmQ1, w));
+    VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+bool window_attention_tc80_supported(const AttnArgs& a, int head_dim) {
+    return head_dim == h80::HD && a.qmap.mode == 1 && a.qmap.win == h80::HWIN && a.qmap.grid % h80::HWIN == 0 && a.Sq == h80::HSK &&
+           a.Sk == h80::HSK && a.q == a.k && a.q == a.v && a.ldq == a.ldk && a.ldq == a.ldv && a.ldq % 8 == 0 && a.ldo % 8 == 0 &&
+           a.qoff % 8 == 0 && a.koff % 8 == 0 && a.voff % 8 == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(a.o) & 15) == 0;
+}
+
+int window_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream) {
+    using namespace h80;
+    if (int rc = init()) return rc;
+    const int grid = a.qmap.grid, nws = grid / HWIN, images = a.nprob / (nws * nws);
+    VPU_REQUIRE(images * nws * nws == a.nprob, "window attention: nprob must be images * windows");
+    CUtensorMap tmQm, tmQt, tmKm, tmKt;
+    if (int rc = make_map_w(&tmQm, a.q, a.ldq, images, grid, HWIN, HQ_IROWS, HM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_w(&tmQt, a.q, a.ldq, images, grid, HWIN, HQ_IROWS, HT, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+    if (int rc = make_map_w(&tmKm, a.q, a.ldq, images, grid, HWIN, HWIN, HM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_w(&tmKt, a.q, a.ldq, images, grid, HWIN, HWIN, HT, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+    WinArgs w;
+    w.o = a.o; w.ldo = a.ldo; w.heads = a.heads; w.nwin_side = nws; w.grid = grid; w.tokens = a.qmap.tokens;
+    w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
+    const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
+    VPU_CHECK_CUDA(launch_pdl(window_attention_tc80_kernel, dim3(ctas), dim3(THREADS), SMEM, stream, tmQm, tmQt, tmKm, tmKt, w));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -144,6 +144,32 @@ def test_window_attention_tcgen05_many_problems():
     assert (o.float() - refw).abs().max().item() < 1e-2 * max(1.0, refw.abs().max().item())
 
 
+@pytest.mark.parametrize("B,amp", [(1, 1.0), (12, 2.0)])
+def test_window_attention_tcgen05_vit_huge(B, amp):
+    """ViT-H window attention (16x16 windows, d=80 = a 128-byte-swizzled 64-column part + a 32-byte-swizzled 16-column
+    part per operand) on the tcgen05/TMEM kernel: fewer problems than SMs (B=1) and the multi-problem loop with the
+    split Q/K and V rings (B=12: 768 problems).  A per-head-dim-column probe (V = one-hot columns) pins the column order
+    of both output parts."""
+    from pvpuformer_b200 import ops
+    heads, hd, grid, win = 16, 80, 32, 16
+    N, C = grid * grid, heads * hd
+    qkv = _rand_bf16((B * N, 3 * C), 41 + B, amp)
+    scale = hd ** -0.5
+    t = qkv.view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    nw = grid // win
+
+    def part(x):
+        x = x.reshape(B, heads, nw, win, nw, win, hd).permute(0, 2, 4, 1, 3, 5, 6)
+        return x.reshape(B * nw * nw, heads, win * win, hd)
+    refw = _attn_ref(part(t[0]), part(t[1]), part(t[2]), scale)
+    refw = refw.reshape(B, nw, nw, heads, win, win, hd).permute(0, 1, 4, 2, 5, 3, 6).reshape(B * N, C)
+    o = ops.attention(qkv, qkv, qkv, win * win, win * win, heads, hd, B * nw * nw, scale, 0, C, 2 * C, window=win, grid=grid)
+    torch.cuda.synchronize()
+    assert not torch.isnan(o.float()).any()
+    err = (o.float() - refw).abs()
+    assert err.max().item() < 1e-2 * max(1.0, refw.abs().max().item()), (err.max().item(), err.view(B * N, heads, hd).amax((0, 1)))
+
+
 @pytest.mark.parametrize("heads,B,amp", [(12, 20, 1.0), (16, 5, 6.0)])
 def test_global_attention_tcgen05_many_problems(heads, B, amp):
     """ViT-B / ViT-L global attention (S=784, d=64) on the tcgen05 flash kernel with more work units than SMs (every

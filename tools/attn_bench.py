@@ -36,6 +36,18 @@ def main():
     ms = timeit(lambda: ops.attention(qkv, qkv, qkv, N, N, heads, hd, B, scale, 0, C, 2 * C))
     fl = 4.0 * N * N * hd * heads * B
     print("vit global  %8.1f us  %7.1f TF/s  %7.1f GB/s" % (ms * 1e3, fl / ms / 1e9, by / ms / 1e6))
+    if os.environ.get("ATTN_BENCH_VITH", "1") != "0":
+        Bh, hh, dh, gh, wh = 32, 16, 80, 32, 16
+        Nh, Ch = gh * gh, hh * dh
+        qh = (torch.randn(Bh * Nh, 3 * Ch, device=dev)).to(torch.bfloat16)
+        byh = Bh * Nh * Ch * 2 * 4.0
+        ms = timeit(lambda: ops.attention(qh, qh, qh, wh * wh, wh * wh, hh, dh, Bh * 4, dh ** -0.5, 0, Ch, 2 * Ch, window=wh, grid=gh))
+        fl = 4.0 * 256 * 256 * dh * hh * Bh * 4
+        print("vit-h window %7.1f us  %7.1f TF/s  %7.1f GB/s" % (ms * 1e3, fl / ms / 1e9, byh / ms / 1e6))
+        ms = timeit(lambda: ops.attention(qh, qh, qh, Nh, Nh, hh, dh, Bh, dh ** -0.5, 0, Ch, 2 * Ch))
+        fl = 4.0 * Nh * Nh * dh * hh * Bh
+        print("vit-h global %7.1f us  %7.1f TF/s  %7.1f GB/s" % (ms * 1e3, fl / ms / 1e9, byh / ms / 1e6))
+        del qh
     Ci, Q, H = C // 2, 48, 8
     tq = torch.randn(B * Q, Ci, device=dev).to(torch.bfloat16)
     kvq = torch.randn(B * N, 3 * Ci, device=dev).to(torch.bfloat16)
