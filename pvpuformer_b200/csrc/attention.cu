@@ -256,6 +256,7 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
     static const bool use_tc = [] { const char* e = getenv("VPU_ATTN_TC"); return !(e && e[0] == '0'); }();
     if (use_tc && window_attention_tc_supported(a, head_dim)) return window_attention_tc_launch(a, stream);
     if (use_tc && window_attention_tc80_supported(a, head_dim)) return window_attention_tc80_launch(a, stream);
+    if (use_tc && global_attention_tc80_supported(a, head_dim)) return global_attention_tc80_launch(a, stream);
     if (use_tc && global_attention_tc_supported(a, head_dim)) return global_attention_tc_launch(a, stream);
     switch (head_dim) {
         case 48: return launch_att<48>(a, stream);

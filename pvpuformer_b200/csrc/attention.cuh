@@ -37,6 +37,9 @@ int window_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream);
 // tcgen05 / TMEM flash kernel for un-windowed self-attention, head_dim 64, S a multiple of 112 (attention_tc.cu)
 bool global_attention_tc_supported(const AttnArgs& a, int head_dim);
 int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
+// same for head_dim 80, S a multiple of 64 (ViT-H; attention_tc.cu)
+bool global_attention_tc80_supported(const AttnArgs& a, int head_dim);
+int global_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream);
 // measurement only: CTA 0 of the next global-attention launches logs (event << 56 | clock64) into dev_buf[4 roles][cap]
 void attention_debug_trace(unsigned long long* dev_buf, int cap);
 

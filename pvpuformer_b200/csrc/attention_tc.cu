@@ -1028,6 +1028,312 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
     }
 }
 
+// =====================================================================================================
+// ViT-H global self-attention (blocks 8 / 16 / 24 / 32): S = 1024 tokens, head_dim 80.
+// The flash kernel above with the 64 + 16 column operand split of the ViT-H window kernel: key blocks of 64
+// (1024 = 16 x 64, no masking; S 64 + P 32 + O 80 TMEM columns per query tile), six K/V stages.
+// =====================================================================================================
+namespace g80 {
+constexpr int KB = 64, QT = 128, HD = 80, HM = 64, HT = 16;
+constexpr int Q_MAIN = QT * HM * 2, Q_TAIL = QT * HT * 2, Q_TILE = Q_MAIN + Q_TAIL;          // 16 + 4 KB
+constexpr int KV_MAIN = KB * HM * 2, KV_TAIL = KB * HT * 2, KV_BLK = KV_MAIN + KV_TAIL;      // 8 + 2 KB
+constexpr int STG_B = 2 * KV_BLK, NSTG = 6;
+constexpr int KV_OFF = 4 * Q_TILE;
+constexpr int SMEM = KV_OFF + NSTG * STG_B + 1024;
+constexpr int P_COL = 64, O_MAIN_COL = 96, O_TAIL_COL = 160;
+static_assert(Q_TILE % 1024 == 0 && KV_MAIN % 1024 == 0 && KV_BLK % 1024 == 0, "swizzle atoms must stay aligned");
+}  // namespace g80
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+global_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmQt,
+                             const __grid_constant__ CUtensorMap tmKm, const __grid_constant__ CUtensorMap tmKt, const GlobArgs a) {
+    using namespace g80;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t q_full[2], q_empty[2], kv_full[NSTG], kv_empty[NSTG], s_full[2], s_free[2], p_full[2], pv_done[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQm);
+        tma_prefetch_desc(&tmQt);
+        tma_prefetch_desc(&tmKm);
+        tma_prefetch_desc(&tmKt);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 2);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 4);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&pv_done[i], 1);
+        }
+        for (int s = 0; s < NSTG; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 2);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+    const int last_tile_pair = a.npairs - 1;
+    const bool odd_tiles = (a.ntiles & 1) != 0;
+
+    if (warp == 0) {
+        // ---------------- TMA producer (converged warp, one elected lane) ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int u = blockIdx.x; u < a.nunits; u += gridDim.x, ++it) {
+            const int pr = u % a.npairs, bh = u / a.npairs, h = bh % a.heads, b = bh / a.heads;
+            const bool two = !(odd_tiles && pr == last_tile_pair);
+            const int qb = it & 1;
+            const int qc = a.qcol + h * HD, kc = a.kcol + h * HD, vc = a.vcol + h * HD;
+            mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&q_full[qb], (two ? 2 : 1) * Q_TILE);
+                uint8_t* qs = smem + qb * 2 * Q_TILE;
+                const int r0 = b * a.S + (2 * pr) * QT;
+                tma_load_2d(qs, &tmQm, &q_full[qb], qc, r0);
+                tma_load_2d(qs + Q_MAIN, &tmQt, &q_full[qb], qc + HM, r0);
+                if (two) {
+                    tma_load_2d(qs + Q_TILE, &tmQm, &q_full[qb], qc, r0 + QT);
+                    tma_load_2d(qs + Q_TILE + Q_MAIN, &tmQt, &q_full[qb], qc + HM, r0 + QT);
+                }
+            }
+            __syncwarp();
+            for (int j = 0; j < a.nblocks; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&kv_full[stage], STG_B);
+                    uint8_t* st = smem + KV_OFF + stage * STG_B;
+                    const int r = b * a.S + j * KB;
+                    tma_load_2d(st, &tmKm, &kv_full[stage], kc, r);
+                    tma_load_2d(st + KV_MAIN, &tmKt, &kv_full[stage], kc + HM, r);
+                    tma_load_2d(st + KV_BLK, &tmKm, &kv_full[stage], vc, r);
+                    tma_load_2d(st + KV_BLK + KV_MAIN, &tmKt, &kv_full[stage], vc + HM, r);
+                }
+                __syncwarp();
+                if (++stage == NSTG) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 || warp == G_MMA1_WARP) {
+        // ---------------- MMA issuers: one warp per query tile ----------------
+        const int t = warp == 1 ? 0 : 1;
+        constexpr uint32_t idesc_s = idesc_bf16(128, KB, false);
+        constexpr uint32_t idesc_om = idesc_bf16(128, HM, true), idesc_ot = idesc_bf16(128, HT, true);
+        const uint32_t s_tmem = tmem_base + t * TILE_COLS, p_tmem = s_tmem + P_COL;
+        const uint64_t qm0 = umma_desc_k_sw128(smem_base + t * Q_TILE), qt0 = umma_desc_sw32(smem_base + t * Q_TILE + Q_MAIN);
+        const uint64_t km0 = umma_desc_k_sw128(smem_base + KV_OFF), kt0 = umma_desc_sw32(smem_base + KV_OFF + KV_MAIN);
+        const uint64_t vm0 = umma_desc_mn_sw128(smem_base + KV_OFF + KV_BLK), vt0 = umma_desc_sw32(smem_base + KV_OFF + KV_BLK + KV_MAIN);
+        auto issue_s = [&](int qb, int st) {
+            if (elect_one()) {
+                const uint64_t qo = (uint64_t)(qb * (2 * Q_TILE >> 4)), ko = (uint64_t)(st * (STG_B >> 4));
+#pragma unroll
+                for (int k = 0; k < HM / 16; ++k) umma_bf16(s_tmem, qm0 + qo + 2 * k, km0 + ko + 2 * k, idesc_s, k ? 1u : 0u);
+                umma_bf16(s_tmem, qt0 + qo, kt0 + ko, idesc_s, 1u);
+                umma_commit(&s_full[t]);
+            }
+            __syncwarp();
+        };
+        int stage = 0;
+        uint32_t phase = 0, pph = 0, fph = 0;
+        int it = 0;
+        int u = blockIdx.x;
+        if (u < a.nunits && (t == 0 || !(odd_tiles && (u % a.npairs) == last_tile_pair))) {
+            mbar_wait(&q_full[0], 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+        }
+        for (; u < a.nunits; u += gridDim.x, ++it) {
+            const bool two = !(odd_tiles && (u % a.npairs) == last_tile_pair);
+            const bool valid = t == 0 || two;
+            const int un = u + (int)gridDim.x;
+            const bool valid_next = un < a.nunits && (t == 0 || !(odd_tiles && (un % a.npairs) == last_tile_pair));
+            const int ncommit = (t == 0 && !two) ? 2 : 1;
+            for (int j = 0; j < a.nblocks; ++j) {
+                const int nstage = (stage + 1 == NSTG) ? 0 : stage + 1;
+                const uint32_t nphase = (stage + 1 == NSTG) ? phase ^ 1 : phase;
+                const bool last = j + 1 == a.nblocks;
+                if (valid) {
+                    mbar_wait(&s_free[t], fph);
+                    fph ^= 1;
+                }
+                if (last ? valid_next : valid) {
+                    if (last) mbar_wait(&q_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+                    mbar_wait(&kv_full[nstage], nphase);
+                    tc_fence_after();
+                    issue_s(last ? (it + 1) & 1 : it & 1, nstage);
+                }
+                if (valid) {
+                    mbar_wait(&p_full[t], pph);
+                    pph ^= 1;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t vo = (uint64_t)(stage * (STG_B >> 4));
+#pragma unroll
+                        for (int k = 0; k < KB / 16; ++k) {
+                            const uint32_t acc = (j == 0 && k == 0) ? 0u : 1u;
+                            umma_bf16_ts(s_tmem + O_MAIN_COL, p_tmem + k * 8, vm0 + vo + 128 * k, idesc_om, acc);
+                            umma_bf16_ts(s_tmem + O_TAIL_COL, p_tmem + k * 8, vt0 + vo + 32 * k, idesc_ot, acc);
+                        }
+                        umma_commit(&pv_done[t]);
+                        umma_commit(&kv_empty[stage]);
+                        if (ncommit == 2) umma_commit(&kv_empty[stage]);
+                        if (last) {
+                            umma_commit(&q_empty[it & 1]);
+                            if (ncommit == 2) umma_commit(&q_empty[it & 1]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                stage = nstage;
+                phase = nphase;
+            }
+        }
+    } else {  // ---------------- softmax + epilogue warpgroups ----------------
+        const int t = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t tile_tmem = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * TILE_COLS;
+        uint32_t sph = 0, vph = 0;
+        for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+            const int pr = u % a.npairs, bh = u / a.npairs, h = bh % a.heads, b = bh / a.heads;
+            if (t == 1 && odd_tiles && pr == last_tile_pair) continue;
+            const int q0 = (2 * pr + t) * QT;
+            float m = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            for (int j = 0; j < a.nblocks; ++j) {
+                mbar_wait(&s_full[t], sph);
+                sph ^= 1;
+                tc_fence_after();
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(tile_tmem, r0);
+                tmem_ld_32x32(tile_tmem + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[t]);      // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
+                bool rescale = false;
+                float alpha = 1.0f;
+                uint32_t pk[16];
+                const float sc = a.scale_log2;
+                auto expo = [&](uint32_t sbits) { return ex2_approx(fmaf(__uint_as_float(sbits), sc, -m)); };
+                {
+                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3])));
+                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])));
+                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3])));
+                    }
+                    const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+                    if (j == 0) {
+                        m = mb;
+                    } else {
+                        const bool need = mb - m > 8.0f;
+                        rescale = __any_sync(0xffffffffu, need) != 0;
+                        if (rescale) {
+                            alpha = need ? ex2_approx(m - mb) : 1.0f;
+                            if (need) m = mb;
+                            l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float p0 = expo(r0[2 * i]), p1 = expo(r0[2 * i + 1]), p2 = expo(r0[2 * i + 2]), p3 = expo(r0[2 * i + 3]);
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        pk[i] = pack_bf16(p0, p1); pk[i + 1] = pack_bf16(p2, p3);
+                    }
+                }
+                if (j > 0) {     // P V(j-1) complete: P may be overwritten, O rescaled
+                    mbar_wait(&pv_done[t], vph);
+                    vph ^= 1;
+                    tc_fence_after();
+                }
+                if (rescale) {
+#pragma unroll 1
+                    for (int c = 0; c < 3; ++c) {
+                        uint32_t o[32];
+                        if (c < 2) {
+                            tmem_ld_32x32(tile_tmem + O_MAIN_COL + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_32x32(tile_tmem + O_MAIN_COL + c * 32, o);
+                        } else {
+                            uint32_t o16[16];
+                            tmem_ld_32x16(tile_tmem + O_TAIL_COL, o16);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
+                            tmem_st_32x16(tile_tmem + O_TAIL_COL, o16);
+                        }
+                    }
+                }
+                tmem_st_32x16(tile_tmem + P_COL, pk);
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float p0 = expo(r1[2 * i]), p1 = expo(r1[2 * i + 1]), p2 = expo(r1[2 * i + 2]), p3 = expo(r1[2 * i + 3]);
+                    l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                    pk[i] = pack_bf16(p0, p1); pk[i + 1] = pack_bf16(p2, p3);
+                }
+                tmem_st_32x16(tile_tmem + P_COL + 16, pk);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);
+            }
+            // epilogue: O / l -> bf16 -> token-major output row of this query
+            mbar_wait(&pv_done[t], vph);
+            vph ^= 1;
+            tc_fence_after();
+            const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+            __nv_bfloat16* dst = a.o + ((size_t)b * a.S + q0 + row) * a.ldo + h * HD;
+            auto store8 = [&](__nv_bfloat16* d, const uint32_t* r) {
+                uint4 v;
+                v.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+                v.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+                v.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+                v.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+                *reinterpret_cast<uint4*>(d) = v;
+            };
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tile_tmem + O_MAIN_COL + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) store8(dst + c * 32 + qq * 8, r + 8 * qq);
+            }
+            {
+                uint32_t r[16];
+                tmem_ld_32x16(tile_tmem + O_TAIL_COL, r);
+                tmem_ld_wait();
+                store8(dst + HM, r);
+                store8(dst + HM + 8, r + 8);
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---- host: 5-D tensor maps over the fused projection buffer --------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1065,6 +1371,7 @@ int init() {
     VPU_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     VPU_CHECK_CUDA(cudaFuncSetAttribute(global_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
     VPU_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h80::SMEM));
+    VPU_CHECK_CUDA(cudaFuncSetAttribute(global_attention_tc80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g80::SMEM));
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
@@ -1094,9 +1401,9 @@ int make_map(CUtensorMap* tm, const void* ptr, int ld, int images, int grid, int
     return make_map_w(tm, ptr, ld, images, grid, WIN, irows, D, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-// plain 2-D map over a token-major [rows, ld] bf16 buffer: box = 64 columns x box_rows rows, 128B swizzle
-int make_map_2d(CUtensorMap* tm, const void* ptr, int ld, long long rows, int box_rows) {
-    Key key{ptr, ld, (int)rows, box_rows, -1};
+// plain 2-D map over a token-major [rows, ld] bf16 buffer: box = cols columns x box_rows rows
+int make_map_2d_w(CUtensorMap* tm, const void* ptr, int ld, long long rows, int box_rows, int cols, CUtensorMapSwizzle swz) {
+    Key key{ptr, ld, (int)rows, box_rows, -1 - (cols << 4) - (int)swz};
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_cache.find(key);
@@ -1104,16 +1411,18 @@ int make_map_2d(CUtensorMap* tm, const void* ptr, int ld, long long rows, int bo
     }
     cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)D, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VPU_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (2-D attention map) failed with %d", (int)r);
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_cache.size() > 1024) g_cache.clear();
     g_cache[key] = *tm;
     return 0;
+}
+int make_map_2d(CUtensorMap* tm, const void* ptr, int ld, long long rows, int box_rows) {
+    return make_map_2d_w(tm, ptr, ld, rows, box_rows, D, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace
@@ -1199,6 +1508,37 @@ int window_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream) {
     w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
     const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
     VPU_CHECK_CUDA(launch_pdl(window_attention_tc80_kernel, dim3(ctas), dim3(THREADS), SMEM, stream, tmQm, tmQt, tmKm, tmKt, w));
+    VPU_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+bool global_attention_tc80_supported(const AttnArgs& a, int head_dim) {
+    return head_dim == g80::HD && a.qmap.mode == 0 && a.kmap.mode == 0 && a.Sq == a.Sk && a.Sk % g80::QT == 0 && a.k == a.v && a.ldk == a.ldv &&
+           a.qmap.per_prob == a.Sq && a.kmap.per_prob == a.Sk && a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 &&
+           a.ldo % 8 == 0 && a.qoff % 8 == 0 && a.koff % 8 == 0 && a.voff % 8 == 0 &&
+           ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
+             reinterpret_cast<uintptr_t>(a.o)) & 15) == 0;
+}
+
+int global_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream) {
+    using namespace g80;
+    if (int rc = init()) return rc;
+    const long long rows = (long long)a.nprob * a.Sq;
+    CUtensorMap tmQm, tmQt, tmKm, tmKt;
+    VPU_REQUIRE(a.k == a.v && a.ldk == a.ldv, "ViT-H global attention expects K and V in one buffer");
+    if (int rc = make_map_2d_w(&tmQm, a.q, a.ldq, rows, QT, HM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_2d_w(&tmQt, a.q, a.ldq, rows, QT, HT, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+    if (int rc = make_map_2d_w(&tmKm, a.k, a.ldk, rows, KB, HM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_2d_w(&tmKt, a.k, a.ldk, rows, KB, HT, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+    GlobArgs g;
+    g.o = a.o; g.ldo = a.ldo; g.heads = a.heads; g.S = a.Sq; g.nblocks = a.Sk / KB;
+    g.ntiles = (a.Sq + QT - 1) / QT; g.npairs = (g.ntiles + 1) / 2;
+    g.nunits = a.nprob * a.heads * g.npairs;
+    g.qcol = a.qoff; g.kcol = a.koff; g.vcol = a.voff; g.scale_log2 = a.scale_log2;
+    g.ablate = 0; g.trace = nullptr; g.trace_cap = 0;
+    const int ctas = g.nunits < g_sms ? g.nunits : g_sms;
+    VPU_CHECK_CUDA(launch_pdl(global_attention_tc80_kernel, dim3(ctas), dim3(G_THREADS), SMEM, stream, tmQm, tmQt, tmKm, tmKt, g));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -170,6 +170,26 @@ def test_window_attention_tcgen05_vit_huge(B, amp):
     assert err.max().item() < 1e-2 * max(1.0, refw.abs().max().item()), (err.max().item(), err.view(B * N, heads, hd).amax((0, 1)))
 
 
+@pytest.mark.parametrize("B,amp", [(3, 1.0), (5, 6.0)])
+def test_global_attention_tcgen05_vit_huge(B, amp):
+    """ViT-H global attention (S=1024, d=80) on the tcgen05 flash kernel with the 64 + 16 column operand split and 16 key
+    blocks of 64; more work units than SMs, and (amp=6) block maxima far enough apart for the lazy O / l rescale."""
+    from pvpuformer_b200 import ops
+    heads, hd, N = 16, 80, 1024
+    C = heads * hd
+    qkv = _rand_bf16((B * N, 3 * C), 51 + B, amp)
+    if amp > 1.0:
+        qkv.view(B, N, 3 * C)[:, : N // 2, C:2 * C] *= 0.05
+    scale = hd ** -0.5
+    t = qkv.view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    ref = _attn_ref(t[0], t[1], t[2], scale).transpose(1, 2).reshape(B * N, C)
+    o = ops.attention(qkv, qkv, qkv, N, N, heads, hd, B, scale, 0, C, 2 * C)
+    torch.cuda.synchronize()
+    assert not torch.isnan(o.float()).any()
+    err = (o.float() - ref).abs()
+    assert err.max().item() < 1e-2 * max(1.0, ref.abs().max().item()), (err.max().item(), err.view(B * N, heads, hd).amax((0, 1)))
+
+
 @pytest.mark.parametrize("heads,B,amp", [(12, 20, 1.0), (16, 5, 6.0)])
 def test_global_attention_tcgen05_many_problems(heads, B, amp):
     """ViT-B / ViT-L global attention (S=784, d=64) on the tcgen05 flash kernel with more work units than SMs (every
