@@ -385,6 +385,7 @@ constexpr int G_STAGE_BYTES = 2 * G_KV_BYTES;        // K block + V block
 constexpr int G_STAGES = 4;
 constexpr int G_SMEM_BYTES = 2 * 2 * G_Q_BYTES + G_STAGES * G_STAGE_BYTES + 1024;
 constexpr int G_P_COL = 112, G_O_COL = 192;
+static_assert(G_SMEM_BYTES <= 232448 && SMEM_BYTES <= 232448, "dynamic shared memory limit of sm_100");
 constexpr int G_MMA1_WARP = 10;                      // warp 0 TMA, 1 MMA tile 0, 2-5 / 6-9 softmax tile 0 / 1, 10 MMA tile 1
 constexpr int G_THREADS = 352;
 
@@ -474,28 +475,33 @@ global_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const bool odd_tiles = (a.ntiles & 1) != 0;      // the last pair of every problem holds a single tile
 
     if (warp == 0) {
-        if (lane == 0) {  // ---------------- TMA producer ----------------
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int u = blockIdx.x; u < a.nunits; u += gridDim.x, ++it) {
-                const int pr = u % a.npairs, bh = u / a.npairs, h = bh % a.heads, b = bh / a.heads;
-                const bool two = !(odd_tiles && pr == last_tile_pair);
-                const int qb = it & 1;
-                mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        // ---------------- TMA producer (converged warp, one elected lane issues) ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int u = blockIdx.x; u < a.nunits; u += gridDim.x, ++it) {
+            const int pr = u % a.npairs, bh = u / a.npairs, h = bh % a.heads, b = bh / a.heads;
+            const bool two = !(odd_tiles && pr == last_tile_pair);
+            const int qb = it & 1;
+            mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&q_full[qb], (two ? 2 : 1) * G_Q_BYTES);
                 uint8_t* qs = smem + qb * 2 * G_Q_BYTES;
                 tma_load_2d(qs, &tmQ, &q_full[qb], a.qcol + h * D, b * a.S + (2 * pr) * G_QT);
                 if (two) tma_load_2d(qs + G_Q_BYTES, &tmQ, &q_full[qb], a.qcol + h * D, b * a.S + (2 * pr + 1) * G_QT);
-                for (int j = 0; j < a.nblocks; ++j) {
-                    mbar_wait(&kv_empty[stage], phase ^ 1);
-                    G_TRACE(0, 1);
+            }
+            __syncwarp();
+            for (int j = 0; j < a.nblocks; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                G_TRACE(0, 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&kv_full[stage], G_STAGE_BYTES);
                     uint8_t* st = smem + KV_OFF + stage * G_STAGE_BYTES;
                     tma_load_2d(st, &tmK, &kv_full[stage], a.kcol + h * D, b * a.S + j * G_KB);
                     tma_load_2d(st + G_KV_BYTES, &tmV, &kv_full[stage], a.vcol + h * D, b * a.S + j * G_KB);
-                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1 || warp == G_MMA1_WARP) {
@@ -769,6 +775,7 @@ constexpr int V_OFF = 2 * QK_STAGE;
 constexpr int SMEM = V_OFF + KV_BUF + 1024;              // 201 KB
 constexpr int O_MAIN_COL = 128, O_TAIL_COL = 192;
 static_assert(Q_MAIN % 1024 == 0 && Q_TILE % 1024 == 0 && KV_MAIN % 1024 == 0 && KV_BUF % 1024 == 0, "swizzle atoms must stay aligned");
+static_assert(SMEM <= 232448, "dynamic shared memory limit of sm_100");
 }  // namespace h80
 
 // 32-byte-swizzled operand part (16 bf16 columns = one 32-byte row, 8-row atoms 256 B apart); the same bits describe the
@@ -1042,6 +1049,7 @@ constexpr int KV_OFF = 4 * Q_TILE;
 constexpr int SMEM = KV_OFF + NSTG * STG_B + 1024;
 constexpr int P_COL = 64, O_MAIN_COL = 96, O_TAIL_COL = 160;
 static_assert(Q_TILE % 1024 == 0 && KV_MAIN % 1024 == 0 && KV_BLK % 1024 == 0, "swizzle atoms must stay aligned");
+static_assert(SMEM <= 232448, "dynamic shared memory limit of sm_100");
 }  // namespace g80
 
 __global__ void __launch_bounds__(G_THREADS, 1)
