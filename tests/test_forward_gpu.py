@@ -196,9 +196,10 @@ def test_full_size_batch_properties_config2():
     """BASELINE.json configs[1] at full size (batch 64, 1..20 clicks per image, the bench workload): the forward is
     deterministic, every checked sample equals its own batch-1 forward bit for bit (which also crosses the small-batch
     programmatic-dependent-launch mode), and two samples are checked against the CPU oracle."""
-    from pvpuformer_b200.synthetic import workload
+    from pvpuformer_b200 import synthetic
     m, sd = _model("vit_base")
-    image4, pts = workload("vit_base", 64, seed=100)
+    image4 = synthetic.images(64, seed=100)                                   # bench.py: make_inputs
+    pts = synthetic.random_clicks(64, seed=101, dtype=torch.float64)
     img_d, pts_d = image4.cuda(), pts.cuda()
     out = m(img_d, pts_d)
     inst, aux = out["instances"].clone(), out["instances_aux"].clone()
