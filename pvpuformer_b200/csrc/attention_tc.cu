@@ -85,6 +85,16 @@ __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU; arguments 
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 16 fp32 accumulators * inv -> 16 bf16 -> one 32-byte global store (STG.256).  An epilogue thread owns one output row, so
+// every store instruction of a warp touches 32 different lines and the L1 store path charges per line touched, not per
+// byte (clock64 trace, round 1i: ten 16-byte stores per thread took 2300 clk per tile): half as many instructions, half the cost.
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const uint32_t* r, float inv) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // MN-major 128B-swizzled operand (V: rows = keys (K), 64 head-dim elements = one 128-byte row):
@@ -103,6 +113,9 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool b_mn_major)
            ((uint32_t)(M >> 4) << 24);
 }
 
+static unsigned long long* g_trace = nullptr;     // vpu_debug_attention_trace
+static int g_trace_cap = 0;
+
 struct WinArgs {
     __nv_bfloat16* o;
     int ldo;
@@ -110,7 +123,18 @@ struct WinArgs {
     int nprob;                            // images * windows * heads
     int qcol, kcol, vcol;                 // column of head 0 in the fused projection buffer
     float scale_log2;
+    unsigned long long* trace;            // measurement only (-DVPU_ATTN_DEBUG + vpu_debug_attention_trace): CTA 0 logs (event << 56 | clock)
+    int trace_cap;
 };
+#ifdef VPU_ATTN_DEBUG
+#define W_TRACE(role, code)                                                                              \
+    do {                                                                                                 \
+        if (a.trace && blockIdx.x == 0 && tr_n < a.trace_cap)                                            \
+            a.trace[(role) * a.trace_cap + tr_n++] = ((unsigned long long)(code) << 56) | (clock64() & 0xFFFFFFFFFFFFFFull); \
+    } while (0)
+#else
+#define W_TRACE(role, code) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(THREADS, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ0,
@@ -321,33 +345,28 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
-            // epilogue: O / rowsum -> bf16 -> token-major output row of this query
+            // epilogue: O / rowsum -> bf16 -> token-major output row of this query.  O goes to registers and the tile's TMEM
+            // columns are released BEFORE the global stores (an mbarrier arrive is a release: it waits for the warp's
+            // outstanding stores, ~2000 clk on the tile's serial chain when they sit in front of it)
             mbar_wait(&o_full[t], tphase);
             tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(tile_tmem + O_COL, o0);
+            tmem_ld_32x32(tile_tmem + O_COL + 32, o1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[t]);
             const float inv = warp_has_rows ? 1.0f / sum : 0.f;
             const int wi = w / a.nwin_side, wj = w % a.nwin_side;
             const int s = (t == 0 ? 0 : T0_ROWS) + row, i = s / WIN, j = s % WIN;
             __nv_bfloat16* dst = a.o + ((size_t)b * a.tokens + (size_t)(wi * WIN + i) * a.grid + wj * WIN + j) * a.ldo + h * D;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tile_tmem + O_COL + c * 32, r);
-                tmem_ld_wait();
-                if (row < nvalid) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(r[8 * q]) * inv, __uint_as_float(r[8 * q + 1]) * inv);
-                        v.y = pack_bf16(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
-                        v.z = pack_bf16(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
-                        v.w = pack_bf16(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = v;
-                    }
-                }
+            if (row < nvalid) {
+                store16_bf16(dst, o0, inv);
+                store16_bf16(dst + 16, o0 + 16, inv);
+                store16_bf16(dst + 32, o1, inv);
+                store16_bf16(dst + 48, o1 + 16, inv);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[t]);
             tphase ^= 1;
         }
     }
@@ -727,15 +746,8 @@ global_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                     tmem_ld_32x32(tile_tmem + G_O_COL + c * 32, r);
                     tmem_ld_wait();
                     if (q < a.S) {
-#pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            uint4 v;
-                            v.x = pack_bf16(__uint_as_float(r[8 * qq]) * inv, __uint_as_float(r[8 * qq + 1]) * inv);
-                            v.y = pack_bf16(__uint_as_float(r[8 * qq + 2]) * inv, __uint_as_float(r[8 * qq + 3]) * inv);
-                            v.z = pack_bf16(__uint_as_float(r[8 * qq + 4]) * inv, __uint_as_float(r[8 * qq + 5]) * inv);
-                            v.w = pack_bf16(__uint_as_float(r[8 * qq + 6]) * inv, __uint_as_float(r[8 * qq + 7]) * inv);
-                            *reinterpret_cast<uint4*>(dst + c * 32 + qq * 8) = v;
-                        }
+                        store16_bf16(dst + c * 32, r, inv);
+                        store16_bf16(dst + c * 32 + 16, r + 16, inv);
                     }
                 }
             }
@@ -802,6 +814,8 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tr_n = 0;
+    (void)tr_n;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQm);
@@ -840,6 +854,7 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             const int wi = w / a.nwin_side, wj = w % a.nwin_side, r0 = wi * HWIN;
             const int qc = a.qcol + h * HD, kc = a.kcol + h * HD, vc = a.vcol + h * HD;
             mbar_wait(&qk_empty[stage], phase ^ 1);
+            if (lane == 0) W_TRACE(0, 1);
             if (elect_one()) {
                 uint64_t* bar = &qk_full[stage];
                 mbar_arrive_expect_tx(bar, QK_STAGE);
@@ -853,6 +868,7 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             }
             __syncwarp();
             mbar_wait(&v_empty, vph ^ 1);           // second P V product of the previous problem complete
+            if (lane == 0) W_TRACE(0, 2);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&v_full, KV_BUF);
                 tma_load_5d(smem + V_OFF, &tmKm, &v_full, vc, 0, wj, r0, b);
@@ -908,22 +924,32 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             const int nstage = stage ^ 1;
             const uint32_t nphase = stage ? phase ^ 1 : phase;
             mbar_wait(&p_full[0], tphase);
+            if (lane == 0) W_TRACE(1, 1);
             mbar_wait(&v_full, tphase);
+            if (lane == 0) W_TRACE(1, 9);
             tc_fence_after();
             issue_pv(0, false);
+            if (lane == 0) W_TRACE(1, 2);
             if (has_next) {
                 mbar_wait(&qk_full[nstage], nphase);
+                if (lane == 0) W_TRACE(1, 10);
                 mbar_wait(&s_empty[0], tphase);
+                if (lane == 0) W_TRACE(1, 3);
                 tc_fence_after();
                 issue_s(0, nstage, false);
+                if (lane == 0) W_TRACE(1, 4);
             }
             mbar_wait(&p_full[1], tphase);
+            if (lane == 0) W_TRACE(1, 5);
             tc_fence_after();
             issue_pv(1, true);
+            if (lane == 0) W_TRACE(1, 6);
             if (has_next) {
                 mbar_wait(&s_empty[1], tphase);
+                if (lane == 0) W_TRACE(1, 7);
                 tc_fence_after();
                 issue_s(1, nstage, true);
+                if (lane == 0) W_TRACE(1, 8);
             }
             stage = nstage;
             phase = nphase;
@@ -939,6 +965,7 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
             mbar_wait(&s_full[t], tphase);
             tc_fence_after();
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 1);
             float sum0 = 0.f, sum1 = 0.f;
             {
                 float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -962,6 +989,7 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
                     }
                 }
                 const float moff = fmaxf(mx0, mx1) * a.scale_log2;
+                if (quarter == 2 && lane == 0) W_TRACE(2 + t, 2);
                 auto expo = [&](uint32_t sbits) { return ex2_approx(fmaf(__uint_as_float(sbits), a.scale_log2, -moff)); };
                 tmem_ld_32x32(tile_tmem, ra);
 #pragma unroll 1
@@ -991,39 +1019,34 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
-            // epilogue: O / rowsum -> bf16 -> token-major output row of this query (80 columns = ten 16-byte stores)
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 3);
+            // epilogue: O / rowsum -> bf16 -> token-major output row of this query (80 columns = ten 16-byte stores).
+            // O is pulled into registers and the tile's TMEM columns are handed back BEFORE the global stores: an mbarrier
+            // arrive has release semantics and does not retire until the warp's outstanding stores have been acknowledged
+            // (~2000 clk with the stores in front of it, clock64 trace of round 1i), which sat on the tile's serial chain.
             mbar_wait(&o_full[t], tphase);
             tc_fence_after();
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 4);
+            uint32_t o0[32], o1[32], o2[16];
+            tmem_ld_32x32(tile_tmem + O_MAIN_COL, o0);
+            tmem_ld_32x32(tile_tmem + O_MAIN_COL + 32, o1);
+            tmem_ld_32x16(tile_tmem + O_TAIL_COL, o2);
+            tmem_ld_wait();
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 6);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[t]);
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 7);
             const float inv = 1.0f / (sum0 + sum1);
             const int wi = w / a.nwin_side, wj = w % a.nwin_side;
             const int s = t * HQT + row, i = s / HWIN, j = s % HWIN;
             __nv_bfloat16* dst = a.o + ((size_t)b * a.tokens + (size_t)(wi * HWIN + i) * a.grid + wj * HWIN + j) * a.ldo + h * HD;
-            auto store8 = [&](__nv_bfloat16* d, const uint32_t* r) {
-                uint4 v;
-                v.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-                v.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-                v.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-                v.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-                *reinterpret_cast<uint4*>(d) = v;
-            };
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tile_tmem + O_MAIN_COL + c * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 4; ++q) store8(dst + c * 32 + q * 8, r + 8 * q);
-            }
-            {
-                uint32_t r[16];
-                tmem_ld_32x16(tile_tmem + O_TAIL_COL, r);
-                tmem_ld_wait();
-                store8(dst + HM, r);
-                store8(dst + HM + 8, r + 8);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[t]);
+            store16_bf16(dst, o0, inv);
+            store16_bf16(dst + 16, o0 + 16, inv);
+            store16_bf16(dst + 32, o1, inv);
+            store16_bf16(dst + 48, o1 + 16, inv);
+            store16_bf16(dst + HM, o2, inv);
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 5);
             tphase ^= 1;
         }
     }
@@ -1308,28 +1331,19 @@ global_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             tc_fence_after();
             const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
             __nv_bfloat16* dst = a.o + ((size_t)b * a.S + q0 + row) * a.ldo + h * HD;
-            auto store8 = [&](__nv_bfloat16* d, const uint32_t* r) {
-                uint4 v;
-                v.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-                v.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-                v.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-                v.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-                *reinterpret_cast<uint4*>(d) = v;
-            };
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(tile_tmem + O_MAIN_COL + c * 32, r);
                 tmem_ld_wait();
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) store8(dst + c * 32 + qq * 8, r + 8 * qq);
+                store16_bf16(dst + c * 32, r, inv);
+                store16_bf16(dst + c * 32 + 16, r + 16, inv);
             }
             {
                 uint32_t r[16];
                 tmem_ld_32x16(tile_tmem + O_TAIL_COL, r);
                 tmem_ld_wait();
-                store8(dst + HM, r);
-                store8(dst + HM + 8, r + 8);
+                store16_bf16(dst + HM, r, inv);
             }
             tc_fence_before();
         }
@@ -1440,11 +1454,10 @@ bool global_attention_tc_supported(const AttnArgs& a, int head_dim) {
            a.qmap.per_prob == a.Sq && a.kmap.per_prob == a.Sk && a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 &&
            a.ldo % 8 == 0 && a.qoff % 8 == 0 && a.koff % 8 == 0 && a.voff % 8 == 0 &&
            ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
-             reinterpret_cast<uintptr_t>(a.o)) & 15) == 0;
+             reinterpret_cast<uintptr_t>(a.o)) & 15) == 0 &&
+           a.ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 31) == 0;      // 32-byte epilogue stores
 }
 
-static unsigned long long* g_trace = nullptr;
-static int g_trace_cap = 0;
 void attention_debug_trace(unsigned long long* dev_buf, int cap) { g_trace = dev_buf; g_trace_cap = cap; }
 
 int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
@@ -1473,7 +1486,7 @@ bool window_attention_tc_supported(const AttnArgs& a, int head_dim) {
     return head_dim == D && a.qmap.mode == 1 && a.qmap.win == WIN && a.qmap.grid % WIN == 0 && a.Sq == SK && a.Sk == SK &&
            a.q == a.k && a.q == a.v && a.ldq == a.ldk && a.ldq == a.ldv && a.ldq % 8 == 0 && a.ldo % 8 == 0 &&
            a.qoff % 8 == 0 && a.koff % 8 == 0 && a.voff % 8 == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 &&
-           (reinterpret_cast<uintptr_t>(a.o) & 15) == 0;
+           a.ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 31) == 0;      // 32-byte epilogue stores
 }
 
 int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
@@ -1487,6 +1500,7 @@ int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
     WinArgs w;
     w.o = a.o; w.ldo = a.ldo; w.heads = a.heads; w.nwin_side = nws; w.grid = grid; w.tokens = a.qmap.tokens;
     w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
+    w.trace = g_trace; w.trace_cap = g_trace_cap;
     const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
     VPU_CHECK_CUDA(launch_pdl(window_attention_tc_kernel, dim3(ctas), dim3(THREADS), SMEM_BYTES, stream, tmKV, tmQ0, tmQ1, w));
     VPU_CHECK_CUDA(cudaGetLastError());
@@ -1498,7 +1512,7 @@ bool window_attention_tc80_supported(const AttnArgs& a, int head_dim) {
     return head_dim == h80::HD && a.qmap.mode == 1 && a.qmap.win == h80::HWIN && a.qmap.grid % h80::HWIN == 0 && a.Sq == h80::HSK &&
            a.Sk == h80::HSK && a.q == a.k && a.q == a.v && a.ldq == a.ldk && a.ldq == a.ldv && a.ldq % 8 == 0 && a.ldo % 8 == 0 &&
            a.qoff % 8 == 0 && a.koff % 8 == 0 && a.voff % 8 == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 &&
-           (reinterpret_cast<uintptr_t>(a.o) & 15) == 0;
+           a.ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 31) == 0;      // 32-byte epilogue stores
 }
 
 int window_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream) {
@@ -1514,6 +1528,7 @@ int window_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream) {
     WinArgs w;
     w.o = a.o; w.ldo = a.ldo; w.heads = a.heads; w.nwin_side = nws; w.grid = grid; w.tokens = a.qmap.tokens;
     w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
+    w.trace = g_trace; w.trace_cap = g_trace_cap;
     const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
     VPU_CHECK_CUDA(launch_pdl(window_attention_tc80_kernel, dim3(ctas), dim3(THREADS), SMEM, stream, tmQm, tmQt, tmKm, tmKt, w));
     VPU_CHECK_CUDA(cudaGetLastError());
@@ -1526,7 +1541,8 @@ bool global_attention_tc80_supported(const AttnArgs& a, int head_dim) {
            a.qmap.per_prob == a.Sq && a.kmap.per_prob == a.Sk && a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 &&
            a.ldo % 8 == 0 && a.qoff % 8 == 0 && a.koff % 8 == 0 && a.voff % 8 == 0 &&
            ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
-             reinterpret_cast<uintptr_t>(a.o)) & 15) == 0;
+             reinterpret_cast<uintptr_t>(a.o)) & 15) == 0 &&
+           a.ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 31) == 0;      // 32-byte epilogue stores
 }
 
 int global_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream) {
