@@ -147,6 +147,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tr_n = 0;
+    (void)tr_n;
 
     // rows 196..207 of every K / V buffer are never written by TMA: zero them once (finite scores, zero P V terms)
     for (int i = threadIdx.x; i < STAGES * 2 * (SKP - SK) * D * 2 / 16; i += THREADS) {
@@ -246,21 +248,30 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
             const uint32_t nphase = (stage + 1 == STAGES) ? phase ^ 1 : phase;
             mbar_wait(&p_full[0], tphase);
+            if (lane == 0) W_TRACE(1, 1);
             tc_fence_after();
             issue_pv(0, stage, false);
+            if (lane == 0) W_TRACE(1, 2);
             if (has_next) {
                 mbar_wait(&full_bar[nstage], nphase);
+                if (lane == 0) W_TRACE(1, 10);
                 mbar_wait(&s_empty[0], tphase);           // tile-0 columns free: epilogue 0 of this problem done
+                if (lane == 0) W_TRACE(1, 3);
                 tc_fence_after();
                 issue_s(0, nstage);
+                if (lane == 0) W_TRACE(1, 4);
             }
             mbar_wait(&p_full[1], tphase);
+            if (lane == 0) W_TRACE(1, 5);
             tc_fence_after();
             issue_pv(1, stage, true);
+            if (lane == 0) W_TRACE(1, 6);
             if (has_next) {
                 mbar_wait(&s_empty[1], tphase);
+                if (lane == 0) W_TRACE(1, 7);
                 tc_fence_after();
                 issue_s(1, nstage);
+                if (lane == 0) W_TRACE(1, 8);
             }
             stage = nstage;
             phase = nphase;
@@ -278,6 +289,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
             mbar_wait(&s_full[t], tphase);
             tc_fence_after();
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 1);
             float sum = 0.f;
             if (warp_has_rows) {      // warps whose 32 rows are all past the tile's valid queries only keep the barriers moving
                 // pass 1: row maximum over the 196 valid keys; the TMEM load of chunk c+1 is in flight while chunk c is reduced
@@ -301,6 +313,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
 #pragma unroll
                 for (int i = 0; i < SK - 192; ++i) mx = fmaxf(mx, __uint_as_float(rt[i]));
                 const float moff = mx * a.scale_log2;
+                if (quarter == 2 && lane == 0) W_TRACE(2 + t, 2);
                 // pass 2: p = exp2(s * scale - max * scale), bf16 pairs written over the already-consumed S columns
                 auto expo = [&](uint32_t sbits) { return ex2_approx(fmaf(__uint_as_float(sbits), a.scale_log2, -moff)); };
                 tmem_ld_32x32(tile_tmem, ra);
@@ -345,11 +358,13 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 3);
             // epilogue: O / rowsum -> bf16 -> token-major output row of this query.  O goes to registers and the tile's TMEM
             // columns are released BEFORE the global stores (an mbarrier arrive is a release: it waits for the warp's
             // outstanding stores, ~2000 clk on the tile's serial chain when they sit in front of it)
             mbar_wait(&o_full[t], tphase);
             tc_fence_after();
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 4);
             uint32_t o0[32], o1[32];
             tmem_ld_32x32(tile_tmem + O_COL, o0);
             tmem_ld_32x32(tile_tmem + O_COL + 32, o1);
@@ -357,6 +372,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[t]);
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 7);
             const float inv = warp_has_rows ? 1.0f / sum : 0.f;
             const int wi = w / a.nwin_side, wj = w % a.nwin_side;
             const int s = (t == 0 ? 0 : T0_ROWS) + row, i = s / WIN, j = s % WIN;
@@ -367,6 +383,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
                 store16_bf16(dst + 32, o1, inv);
                 store16_bf16(dst + 48, o1 + 16, inv);
             }
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 5);
             tphase ^= 1;
         }
     }

@@ -17,7 +17,7 @@ NAMES[3] = NAMES[2]
 
 def main(nshow=80):
     dev = torch.device("cuda:0")
-    B, heads, hd, grid, win = 32, 16, 80, 32, 16
+    B, heads, hd, grid, win = (32, 16, 80, 32, 16) if os.environ.get("ARCH", "h") == "h" else (64, 12, 64, 28, 14)
     N, C = grid * grid, heads * hd
     qkv = torch.randn(B * N, 3 * C, device=dev).to(torch.bfloat16)
     cap = 4096
@@ -72,8 +72,10 @@ def main(nshow=80):
         gaps(role, 3, 4, n + "P stored -> o_full (PV)")
         gaps(role, 4, 6, n + "o_full -> O in registers")
         gaps(role, 6, 7, n + "O in registers -> s_empty arrive")
+        gaps(role, 4, 7, n + "o_full -> s_empty arrive")
         gaps(role, 7, 5, n + "s_empty arrive -> stores issued")
         gaps(role, 5, 1, n + "epilogue done -> next s_full")
+    gaps(1, 1, 2, "MMA p_full[0] -> PV0 issued")
     gaps(1, 1, 9, "MMA p_full[0] -> v_full")
     gaps(1, 9, 2, "MMA v_full -> PV0 issued")
     gaps(1, 2, 10, "MMA PV0 issued -> qk_full next")
