@@ -36,8 +36,10 @@ constexpr int KV_BYTES = SKP * D * 2;                // 26 KB
 constexpr int STAGE_BYTES = 2 * Q_TILE_BYTES + 2 * KV_BYTES;   // 84 KB
 constexpr int STAGES = 2;
 constexpr int TX_BYTES = (T0_ROWS + T1_ROWS + 2 * SK) * D * 2; // bytes the four TMA boxes deliver
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 softmax tile 0, warps 6-9 softmax tile 1
+constexpr int OUT_STAGE_BYTES = 128 * D * 2;                    // 16 KB: one query tile of bf16 output rows, staged for the TMA store
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024;
+constexpr int THREADS = 352;          // warp 0 TMA, warp 1 MMA, warps 2-5 softmax tile 0, warps 6-9 softmax tile 1, warp 10 output TMA stores
+constexpr int STORE_WARP = 10;
 constexpr int TILE_COLS = 256;        // TMEM columns reserved per row tile: S [0,208), P [0,104), O [128,192)
 constexpr int O_COL = 128;
 
@@ -49,6 +51,16 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
         "r"(c4)
         : "memory");
 }
+// shared -> global tile store through a tensor map (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -138,10 +150,11 @@ struct WinArgs {
 
 __global__ void __launch_bounds__(THREADS, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ0,
-                           const __grid_constant__ CUtensorMap tmQ1, const WinArgs a) {
+                           const __grid_constant__ CUtensorMap tmQ1, const __grid_constant__ CUtensorMap tmO0,
+                           const __grid_constant__ CUtensorMap tmO1, const WinArgs a) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], s_full[2], p_full[2], o_full[2], s_empty[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], s_full[2], p_full[2], o_full[2], s_empty[2], stg_full[2], stg_free[2];
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -162,6 +175,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
         tma_prefetch_desc(&tmKV);
         tma_prefetch_desc(&tmQ0);
         tma_prefetch_desc(&tmQ1);
+        tma_prefetch_desc(&tmO0);
+        tma_prefetch_desc(&tmO1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -171,6 +186,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             mbar_init(&p_full[t], 4);
             mbar_init(&o_full[t], 1);
             mbar_init(&s_empty[t], 4);
+            mbar_init(&stg_full[t], 4);
+            mbar_init(&stg_free[t], 1);
         }
         fence_barrier_init();
     }
@@ -277,6 +294,28 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             phase = nphase;
             tphase ^= 1;
         }
+    } else if (warp == STORE_WARP) {
+        // ---------------- output stores: one TMA tensor store per (problem, tile), converged warp, one elected lane ----------------
+        uint32_t tphase = 0;
+        for (int p = blockIdx.x; p < a.nprob; p += gridDim.x) {
+            const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
+            const int wi = w / a.nwin_side, wj = w % a.nwin_side;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(&stg_full[t], tphase);
+                if (elect_one()) {
+                    tma_store_5d(t == 0 ? &tmO0 : &tmO1, smem + STAGES * STAGE_BYTES + t * OUT_STAGE_BYTES, h * D, 0, wj,
+                                 wi * WIN + (t == 0 ? 0 : T0_IROWS), b);
+                    tma_store_commit();
+                    tma_store_wait_read();
+                    mbar_arrive(&stg_free[t]);
+                }
+                __syncwarp();
+            }
+            tphase ^= 1;
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
     } else {  // ---------------- softmax + epilogue warpgroups ----------------
         const int t = (warp - 2) >> 2;                   // row tile of this warpgroup
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
@@ -373,16 +412,30 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[t]);
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 7);
+            // rows -> bf16 -> this tile's staging buffer in the 128-byte-swizzled layout; the store warp sends it with ONE TMA
+            // tensor store through the same 5-D window map shape as the loads.  A thread owns a row, so direct global stores
+            // touch 32 lines per instruction and the L1 store path charges per line: 1300 clk per tile on the serial chain
+            // (clock64 trace, tools/attn_trace_win.py).
             const float inv = warp_has_rows ? 1.0f / sum : 0.f;
-            const int wi = w / a.nwin_side, wj = w % a.nwin_side;
-            const int s = (t == 0 ? 0 : T0_ROWS) + row, i = s / WIN, j = s % WIN;
-            __nv_bfloat16* dst = a.o + ((size_t)b * a.tokens + (size_t)(wi * WIN + i) * a.grid + wj * WIN + j) * a.ldo + h * D;
+            uint8_t* stg = smem + STAGES * STAGE_BYTES + t * OUT_STAGE_BYTES;
+            mbar_wait(&stg_free[t], tphase ^ 1);          // the TMA engine has read the previous problem's rows
+            if (quarter == 2 && lane == 0) W_TRACE(2 + t, 8);
             if (row < nvalid) {
-                store16_bf16(dst, o0, inv);
-                store16_bf16(dst + 16, o0 + 16, inv);
-                store16_bf16(dst + 32, o1, inv);
-                store16_bf16(dst + 48, o1 + 16, inv);
+                uint8_t* rowp = stg + row * (D * 2);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* r = (c < 4 ? o0 : o1) + (c & 3) * 8;
+                    uint4 v;
+                    v.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+                    v.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+                    v.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+                    v.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+                    *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = v;
+                }
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stg_full[t]);
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 5);
             tphase ^= 1;
         }
@@ -801,7 +854,8 @@ constexpr int Q_MAIN = HQT * HM * 2, Q_TAIL = HQT * HT * 2, Q_TILE = Q_MAIN + Q_
 constexpr int KV_MAIN = HSK * HM * 2, KV_TAIL = HSK * HT * 2, KV_BUF = KV_MAIN + KV_TAIL;   // 32 + 8 KB
 constexpr int QK_STAGE = 2 * Q_TILE + KV_BUF;            // 80 KB: two Q tiles + K
 constexpr int V_OFF = 2 * QK_STAGE;
-constexpr int SMEM = V_OFF + KV_BUF + 1024;              // 201 KB
+constexpr int OUT_OFF = V_OFF + KV_BUF;                  // one output staging tile (main + tail part, the Q tile layout) shared by both tiles
+constexpr int SMEM = OUT_OFF + Q_TILE + 1024;            // 221 KB
 constexpr int O_MAIN_COL = 128, O_TAIL_COL = 192;
 static_assert(Q_MAIN % 1024 == 0 && Q_TILE % 1024 == 0 && KV_MAIN % 1024 == 0 && KV_BUF % 1024 == 0, "swizzle atoms must stay aligned");
 static_assert(SMEM <= 232448, "dynamic shared memory limit of sm_100");
@@ -821,11 +875,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmQt,
-                             const __grid_constant__ CUtensorMap tmKm, const __grid_constant__ CUtensorMap tmKt, const WinArgs a) {
+                             const __grid_constant__ CUtensorMap tmKm, const __grid_constant__ CUtensorMap tmKt,
+                             const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmOt, const WinArgs a) {
     using namespace h80;
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t qk_full[2], qk_empty[2], v_full, v_empty, s_full[2], p_full[2], o_full[2], s_empty[2];
+    __shared__ uint64_t qk_full[2], qk_empty[2], v_full, v_empty, s_full[2], p_full[2], o_full[2], s_empty[2], stg_full, stg_free;
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -839,6 +894,8 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
         tma_prefetch_desc(&tmQt);
         tma_prefetch_desc(&tmKm);
         tma_prefetch_desc(&tmKt);
+        tma_prefetch_desc(&tmOm);
+        tma_prefetch_desc(&tmOt);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&qk_full[s], 1);
             mbar_init(&qk_empty[s], 1);
@@ -849,6 +906,8 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
         }
         mbar_init(&v_full, 1);
         mbar_init(&v_empty, 1);
+        mbar_init(&stg_full, 4);
+        mbar_init(&stg_free, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -972,6 +1031,28 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             phase = nphase;
             tphase ^= 1;
         }
+    } else if (warp == STORE_WARP) {
+        // ---------------- output stores: two TMA tensor stores per (problem, tile), converged warp, one elected lane ----------------
+        uint32_t fph = 0;
+        for (int p = blockIdx.x; p < a.nprob; p += gridDim.x) {
+            const int h = p % a.heads, w = (p / a.heads) % nw2, b = p / (a.heads * nw2);
+            const int wi = w / a.nwin_side, wj = w % a.nwin_side;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(&stg_full, fph);
+                fph ^= 1;
+                if (elect_one()) {
+                    tma_store_5d(&tmOm, smem + OUT_OFF, h * HD, 0, wj, wi * HWIN + t * HQ_IROWS, b);
+                    tma_store_5d(&tmOt, smem + OUT_OFF + Q_MAIN, h * HD + HM, 0, wj, wi * HWIN + t * HQ_IROWS, b);
+                    tma_store_commit();
+                    tma_store_wait_read();
+                    mbar_arrive(&stg_free);
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
     } else {  // ---------------- softmax + epilogue warpgroups ----------------
         const int t = (warp - 2) >> 2;
         const int quarter = warp & 3;
@@ -1054,15 +1135,41 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[t]);
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 7);
+            // rows -> bf16 -> staging tile (64-column part 128-byte-swizzled, 16-column part 32-byte-swizzled: the Q tile layout);
+            // the store warp sends it with two TMA tensor stores.  A thread owns a row, so direct global stores touch 32 lines
+            // per instruction and the L1 store path charges per line (1500 clk per tile on the serial chain, clock64 trace).
+            // 201 + 20 KB is all that fits: the two query tiles, which run half a period apart and strictly alternate, share
+            // ONE staging tile (use k = 2 * problem + tile waits for k releases: parity (tile & 1) ^ 1).
             const float inv = 1.0f / (sum0 + sum1);
-            const int wi = w / a.nwin_side, wj = w % a.nwin_side;
-            const int s = t * HQT + row, i = s / HWIN, j = s % HWIN;
-            __nv_bfloat16* dst = a.o + ((size_t)b * a.tokens + (size_t)(wi * HWIN + i) * a.grid + wj * HWIN + j) * a.ldo + h * HD;
-            store16_bf16(dst, o0, inv);
-            store16_bf16(dst + 16, o0 + 16, inv);
-            store16_bf16(dst + 32, o1, inv);
-            store16_bf16(dst + 48, o1 + 16, inv);
-            store16_bf16(dst + HM, o2, inv);
+            uint8_t* stg = smem + OUT_OFF;
+            mbar_wait(&stg_free, (uint32_t)(t ^ 1));
+            {
+                uint8_t* rowm = stg + row * (HM * 2);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* r = (c < 4 ? o0 : o1) + (c & 3) * 8;
+                    uint4 v;
+                    v.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+                    v.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+                    v.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+                    v.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+                    *reinterpret_cast<uint4*>(rowm + ((c ^ (row & 7)) << 4)) = v;
+                }
+                uint8_t* rowt = stg + Q_MAIN + row * (HT * 2);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t* r = o2 + c * 8;
+                    uint4 v;
+                    v.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+                    v.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+                    v.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+                    v.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+                    *reinterpret_cast<uint4*>(rowt + ((c ^ ((row >> 2) & 1)) << 4)) = v;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stg_full);
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 5);
             tphase ^= 1;
         }
@@ -1514,12 +1621,15 @@ int window_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
     if (int rc = make_map(&tmKV, a.q, a.ldq, images, grid, WIN)) return rc;
     if (int rc = make_map(&tmQ0, a.q, a.ldq, images, grid, T0_IROWS)) return rc;
     if (int rc = make_map(&tmQ1, a.q, a.ldq, images, grid, T1_IROWS)) return rc;
+    CUtensorMap tmO0, tmO1;          // output rows of the two query tiles, column 0 = head 0 (a.o has no column offset)
+    if (int rc = make_map(&tmO0, a.o, a.ldo, images, grid, T0_IROWS)) return rc;
+    if (int rc = make_map(&tmO1, a.o, a.ldo, images, grid, T1_IROWS)) return rc;
     WinArgs w;
     w.o = a.o; w.ldo = a.ldo; w.heads = a.heads; w.nwin_side = nws; w.grid = grid; w.tokens = a.qmap.tokens;
     w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
     w.trace = g_trace; w.trace_cap = g_trace_cap;
     const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
-    VPU_CHECK_CUDA(launch_pdl(window_attention_tc_kernel, dim3(ctas), dim3(THREADS), SMEM_BYTES, stream, tmKV, tmQ0, tmQ1, w));
+    VPU_CHECK_CUDA(launch_pdl(window_attention_tc_kernel, dim3(ctas), dim3(THREADS), SMEM_BYTES, stream, tmKV, tmQ0, tmQ1, tmO0, tmO1, w));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -1542,12 +1652,15 @@ int window_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream) {
     if (int rc = make_map_w(&tmQt, a.q, a.ldq, images, grid, HWIN, HQ_IROWS, HT, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
     if (int rc = make_map_w(&tmKm, a.q, a.ldq, images, grid, HWIN, HWIN, HM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_w(&tmKt, a.q, a.ldq, images, grid, HWIN, HWIN, HT, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+    CUtensorMap tmOm, tmOt;          // output rows of a query tile: 64-column and 16-column part
+    if (int rc = make_map_w(&tmOm, a.o, a.ldo, images, grid, HWIN, HQ_IROWS, HM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_w(&tmOt, a.o, a.ldo, images, grid, HWIN, HQ_IROWS, HT, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
     WinArgs w;
     w.o = a.o; w.ldo = a.ldo; w.heads = a.heads; w.nwin_side = nws; w.grid = grid; w.tokens = a.qmap.tokens;
     w.nprob = a.nprob * a.heads; w.qcol = a.qoff; w.kcol = a.koff; w.vcol = a.voff; w.scale_log2 = a.scale_log2;
     w.trace = g_trace; w.trace_cap = g_trace_cap;
     const int ctas = w.nprob < g_sms ? w.nprob : g_sms;
-    VPU_CHECK_CUDA(launch_pdl(window_attention_tc80_kernel, dim3(ctas), dim3(THREADS), SMEM, stream, tmQm, tmQt, tmKm, tmKt, w));
+    VPU_CHECK_CUDA(launch_pdl(window_attention_tc80_kernel, dim3(ctas), dim3(THREADS), SMEM, stream, tmQm, tmQt, tmKm, tmKt, tmOm, tmOt, w));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -74,6 +74,11 @@ def main(nshow=80):
         gaps(role, 6, 7, n + "O in registers -> s_empty arrive")
         gaps(role, 4, 7, n + "o_full -> s_empty arrive")
         gaps(role, 7, 5, n + "s_empty arrive -> stores issued")
+        gaps(role, 7, 8, n + "  s_empty arrive -> staging free (barrier A)")
+        gaps(role, 8, 9, n + "  scale + pack + st.shared")
+        gaps(role, 9, 10, n + "  fence.proxy.async")
+        gaps(role, 10, 11, n + "  barrier B")
+        gaps(role, 11, 5, n + "  TMA store issued")
         gaps(role, 5, 1, n + "epilogue done -> next s_full")
     gaps(1, 1, 2, "MMA p_full[0] -> PV0 issued")
     gaps(1, 1, 9, "MMA p_full[0] -> v_full")
