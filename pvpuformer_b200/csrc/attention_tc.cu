@@ -399,8 +399,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __gri
             if (lane == 0) mbar_arrive(&p_full[t]);
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 3);
             // epilogue: O / rowsum -> bf16 -> token-major output row of this query.  O goes to registers and the tile's TMEM
-            // columns are released BEFORE the global stores (an mbarrier arrive is a release: it waits for the warp's
-            // outstanding stores, ~2000 clk on the tile's serial chain when they sit in front of it)
+            // columns are released BEFORE the rows are written out: the write-out (1300 clk as direct stores, 700 through the
+            // staging tile) is then off the MMA warp's critical path (next S product), clock64 trace of round 1i
             mbar_wait(&o_full[t], tphase);
             tc_fence_after();
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 4);
@@ -1119,9 +1119,9 @@ window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __g
             if (lane == 0) mbar_arrive(&p_full[t]);
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 3);
             // epilogue: O / rowsum -> bf16 -> token-major output row of this query (80 columns = ten 16-byte stores).
-            // O is pulled into registers and the tile's TMEM columns are handed back BEFORE the global stores: an mbarrier
-            // arrive has release semantics and does not retire until the warp's outstanding stores have been acknowledged
-            // (~2000 clk with the stores in front of it, clock64 trace of round 1i), which sat on the tile's serial chain.
+            // O is pulled into registers and the tile's TMEM columns are handed back BEFORE the rows are written out: the
+            // write-out (2300 clk as direct 16-byte stores, 640 through the staging tile) is then off the MMA warp's critical
+            // path to the next S product (clock64 trace of round 1i).
             mbar_wait(&o_full[t], tphase);
             tc_fence_after();
             if (quarter == 2 && lane == 0) W_TRACE(2 + t, 4);
