@@ -10,7 +10,8 @@
 //                        tcgen05.ld, write bf16 P_t back into the same TMEM columns with tcgen05.st
 //   O_t = P_t V          tcgen05.mma with the A operand in TMEM and V as an MN-major shared-memory
 //                        operand (no transpose copy), accumulators aliasing the dead S_t columns
-//   out = O_t / rowsum   tcgen05.ld epilogue, bf16, straight into the token-major attention output
+//   out = O_t / rowsum   tcgen05.ld epilogue -> bf16 rows in a 128-byte-swizzled staging tile -> one TMA tensor store per tile
+//                        (5-D window box, issued by the store warp), so the window un-partition never exists either
 // Scores and probabilities never touch shared or global memory.  The MMA warp software-pipelines
 // S(n+1) between the two P V products of problem n, and Q/K/V of the next problem are prefetched into
 // the second shared-memory stage while the current one is in flight.

@@ -11,7 +11,7 @@ from pvpuformer_b200 import lib as L, ops  # noqa: E402
 NAMES = {0: {1: "qk_empty ok", 2: "v_empty ok"},
          1: {1: "p_full[0]", 9: "v_full", 2: "PV0 issued", 10: "qk_full next", 3: "s_empty[0]", 4: "S0' issued", 5: "p_full[1]", 6: "PV1 issued",
              7: "s_empty[1]", 8: "S1' issued"},
-         2: {1: "s_full", 2: "max done", 3: "P stored + arrive", 4: "o_full", 5: "epilogue done", 6: "O in regs", 7: "s_empty arrive"}}
+         2: {1: "s_full", 2: "max done", 3: "P stored + arrive", 4: "o_full", 5: "epilogue done", 6: "O in regs", 7: "s_empty arrive", 8: "staging tile free"}}
 NAMES[3] = NAMES[2]
 
 
@@ -74,11 +74,8 @@ def main(nshow=80):
         gaps(role, 6, 7, n + "O in registers -> s_empty arrive")
         gaps(role, 4, 7, n + "o_full -> s_empty arrive")
         gaps(role, 7, 5, n + "s_empty arrive -> stores issued")
-        gaps(role, 7, 8, n + "  s_empty arrive -> staging free (barrier A)")
-        gaps(role, 8, 9, n + "  scale + pack + st.shared")
-        gaps(role, 9, 10, n + "  fence.proxy.async")
-        gaps(role, 10, 11, n + "  barrier B")
-        gaps(role, 11, 5, n + "  TMA store issued")
+        gaps(role, 7, 8, n + "  s_empty arrive -> staging tile free")
+        gaps(role, 8, 5, n + "  scale + pack + st.shared + hand-off")
         gaps(role, 5, 1, n + "epilogue done -> next s_full")
     gaps(1, 1, 2, "MMA p_full[0] -> PV0 issued")
     gaps(1, 1, 9, "MMA p_full[0] -> v_full")
