@@ -148,8 +148,8 @@ def test_window_attention_tcgen05_many_problems():
 def test_window_attention_tcgen05_vit_huge(B, amp):
     """ViT-H window attention (16x16 windows, d=80 = a 128-byte-swizzled 64-column part + a 32-byte-swizzled 16-column
     part per operand) on the tcgen05/TMEM kernel: fewer problems than SMs (B=1) and the multi-problem loop with the
-    split Q/K and V rings (B=12: 768 problems).  A per-head-dim-column probe (V = one-hot columns) pins the column order
-    of both output parts."""
+    split Q/K and V rings and the shared output staging tile (B=12: 768 problems).  On failure the assertion message
+    carries the per-head-dim-column error, which separates the 64-column from the 16-column part."""
     from pvpuformer_b200 import ops
     heads, hd, grid, win = 16, 80, 32, 16
     N, C = grid * grid, heads * hd
