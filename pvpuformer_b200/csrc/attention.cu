@@ -7,16 +7,13 @@
 // Round-1 implementation: flash-style online softmax on mma.sync m16n8k16 (bf16 in, fp32
 // accumulate), K/V tiles double-buffered with cp.async, scores never leave registers.
 // Q/K/V are read in place from the projection outputs (row stride + column offset), so no
-// head split / window partition copies exist.  CTA = 4 warps x 16 query rows.
+// head split / window partition copies exist.  CTA = BM / 16 warps x 16 query rows (BM, BN = 64 or 48).
 #include <cstdlib>
 
 #include "attention.cuh"
 
 namespace vpu {
 
-constexpr int ATT_BM = 64;   // query rows per CTA
-constexpr int ATT_BN = 64;   // keys per tile
-constexpr int ATT_THREADS = 128;
 constexpr int ATT_KROW_MAX = 256;   // keys of one window (16 x 16 for ViT-H)
 
 __device__ __forceinline__ int map_row(const RowMap& rm, int prob, int s) {
@@ -60,25 +57,29 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
-template <int D>
-__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a) {
+// BM query rows per CTA (one warp per 16), BN keys per tile: 64 x 64 in general; the DMA shapes have 48 queries and / or 48 keys
+// (transformer.py:499-521 with 24 + 24 prompt tokens), where a 64-wide tile spends a quarter of its MMAs and exponentials on
+// padding, so those launches use 48-row / 48-key tiles (3 warps / 3 k-steps)
+template <int D, int BM, int BN>
+__global__ void __launch_bounds__(BM * 2) attention_kernel(const AttnArgs a) {
+    constexpr int NT = BM * 2;              // threads: one warp per 16 query rows
     pdl_launch_dependents();
     pdl_wait();
     constexpr int PITCH = D + 8;            // +16 B per row: conflict-free ldmatrix
     constexpr int CHUNKS = D / 8;           // 16-byte chunks per row
     extern __shared__ __align__(16) uint8_t att_smem[];
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(att_smem);
-    __nv_bfloat16* Ks = Qs + ATT_BM * PITCH;            // [2][ATT_BN][PITCH]
-    __nv_bfloat16* Vs = Ks + 2 * ATT_BN * PITCH;        // [2][ATT_BN][PITCH]
+    __nv_bfloat16* Ks = Qs + BM * PITCH;            // [2][BN][PITCH]
+    __nv_bfloat16* Vs = Ks + 2 * BN * PITCH;        // [2][BN][PITCH]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, prob = blockIdx.z;
+    const int q0 = blockIdx.x * BM, h = blockIdx.y, prob = blockIdx.z;
     const __nv_bfloat16* qbase = a.q + a.qoff + h * D;
     const __nv_bfloat16* kbase = a.k + a.koff + h * D;
     const __nv_bfloat16* vbase = a.v + a.voff + h * D;
 
     // ---- async loads -------------------------------------------------------------------
-    for (int idx = tid; idx < ATT_BM * CHUNKS; idx += ATT_THREADS) {
+    for (int idx = tid; idx < BM * CHUNKS; idx += NT) {
         const int r = idx / CHUNKS, c = idx % CHUNKS;
         const int s = q0 + r;
         const bool ok = s < a.Sq;
@@ -90,20 +91,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
     __shared__ int krow[ATT_KROW_MAX];
     const bool ktab = a.kmap.mode == 1 && a.Sk <= ATT_KROW_MAX;
     if (ktab) {
-        for (int s = tid; s < a.Sk; s += ATT_THREADS) krow[s] = map_row(a.kmap, prob, s);
+        for (int s = tid; s < a.Sk; s += NT) krow[s] = map_row(a.kmap, prob, s);
         __syncthreads();
     }
     auto load_kv = [&](int tile, int buf) {
-        for (int idx = tid; idx < ATT_BN * CHUNKS; idx += ATT_THREADS) {
+        for (int idx = tid; idx < BN * CHUNKS; idx += NT) {
             const int r = idx / CHUNKS, c = idx % CHUNKS;
-            const int s = tile * ATT_BN + r;
+            const int s = tile * BN + r;
             const bool ok = s < a.Sk;
             const size_t row = ok ? (size_t)(ktab ? krow[s] : map_row(a.kmap, prob, s)) : 0;
-            cp_async16(Ks + (buf * ATT_BN + r) * PITCH + c * 8, kbase + row * a.ldk + c * 8, ok);
-            cp_async16(Vs + (buf * ATT_BN + r) * PITCH + c * 8, vbase + row * a.ldv + c * 8, ok);
+            cp_async16(Ks + (buf * BN + r) * PITCH + c * 8, kbase + row * a.ldk + c * 8, ok);
+            cp_async16(Vs + (buf * BN + r) * PITCH + c * 8, vbase + row * a.ldv + c * 8, ok);
         }
     };
-    const int ntiles = (a.Sk + ATT_BN - 1) / ATT_BN;
+    const int ntiles = (a.Sk + BN - 1) / BN;
     load_kv(0, 0);
     cp_async_commit();
 
@@ -125,17 +126,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         __syncthreads();
 
         // ---- S = Q K^T (16 x 64 per warp) ------------------------------------------------
-        float s[ATT_BN / 8][4];
+        float s[BN / 8][4];
 #pragma unroll
-        for (int i = 0; i < ATT_BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-        const __nv_bfloat16* Kb = Ks + buf * ATT_BN * PITCH;
-        const __nv_bfloat16* Vb = Vs + buf * ATT_BN * PITCH;
+        for (int i = 0; i < BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+        const __nv_bfloat16* Kb = Ks + buf * BN * PITCH;
+        const __nv_bfloat16* Vb = Vs + buf * BN * PITCH;
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
             uint32_t a0, a1, a2, a3;
             ldsm_x4(smem_u32(Qs + (warp * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
 #pragma unroll
-            for (int np = 0; np < ATT_BN / 16; ++np) {
+            for (int np = 0; np < BN / 16; ++np) {
                 uint32_t b0, b1, b2, b3;
                 // matrices: (keys 0-7, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 0-7), (keys 8-15, d 8-15)
                 ldsm_x4(smem_u32(Kb + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * PITCH + ks * 16 + ((lane >> 3) & 1) * 8),
@@ -146,10 +147,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         }
         // ---- mask + online softmax (rows g and g+8 of this warp's 16) ------------------------
         // raw scores: the positive scale commutes with the maximum and is applied inside the exponent's FMA
-        const int kbase_idx = tile * ATT_BN;
-        if (kbase_idx + ATT_BN > a.Sk) {                 // ragged last tile only
+        const int kbase_idx = tile * BN;
+        if (kbase_idx + BN > a.Sk) {                 // ragged last tile only
 #pragma unroll
-            for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+            for (int nt = 0; nt < BN / 8; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     if (kbase_idx + nt * 8 + 2 * t + (e & 1) >= a.Sk) s[nt][e] = -INFINITY;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         }
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-        for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+        for (int nt = 0; nt < BN / 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
         }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         }
         float psum[2] = {0.f, 0.f};
 #pragma unroll
-        for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+        for (int nt = 0; nt < BN / 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float p = ex2_fast(fmaf(s[nt][e], sl2, -mrow[e >> 1]));
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
         }
         // ---- O += P V ---------------------------------------------------------------------
 #pragma unroll
-        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+        for (int kk = 0; kk < BN / 16; ++kk) {
             const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
             const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
             const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
@@ -232,19 +233,28 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs a
     }
 }
 
-template <int D>
-static int launch_att(const AttnArgs& a, cudaStream_t stream) {
-    const int smem = (ATT_BM + 4 * ATT_BN) * (D + 8) * 2;
+template <int D, int BM, int BN>
+static int launch_att_t(const AttnArgs& a, cudaStream_t stream) {
+    const int smem = (BM + 4 * BN) * (D + 8) * 2;
     static bool attr_set = false;
     if (!attr_set) {
-        VPU_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VPU_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<D, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    dim3 grid((a.Sq + ATT_BM - 1) / ATT_BM, a.heads, a.nprob);
-    VPU_CHECK_CUDA(launch_pdl(attention_kernel<D>, dim3(grid), dim3(ATT_THREADS), smem, stream, a));
+    dim3 grid((a.Sq + BM - 1) / BM, a.heads, a.nprob);
+    VPU_CHECK_CUDA(launch_pdl(attention_kernel<D, BM, BN>, dim3(grid), dim3(BM * 2), smem, stream, a));
     VPU_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
+}
+template <int D>
+static int launch_att(const AttnArgs& a, cudaStream_t stream) {
+    static const bool narrow = [] { const char* e = getenv("VPU_ATTN_NARROW"); return !(e && e[0] == '0'); }();
+    const bool q48 = narrow && a.Sq <= 48, k48 = narrow && a.Sk <= 48;
+    if (q48 && k48) return launch_att_t<D, 48, 48>(a, stream);
+    if (q48) return launch_att_t<D, 48, 64>(a, stream);
+    if (k48) return launch_att_t<D, 64, 48>(a, stream);
+    return launch_att_t<D, 64, 64>(a, stream);
 }
 
 int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
