@@ -170,6 +170,11 @@ int vpu_session_prepare(const vpu_session_state* st, const int32_t* active, int 
                         float* net_image, double* net_points, void* stream);
 /* After the forward: logits [2A,1,T,T] (rows a and A + a) -> prev_probs, pred and fgbox of session active[a]. */
 int vpu_session_finish(const vpu_session_state* st, const int32_t* active, int A, const float* logits, void* stream);
+/* ToTensor of the predictor for a whole batch on the device (replaces transforms.ToTensor() of
+ * isegm/inference/predictors/base.py:30,45 and the torch.cat with the previous mask of base.py:113-115): rgb_nhwc uint8 [B,H,W,3],
+ * prev_mask fp32 [B,H,W] or NULL (zeros) -> image4 fp32 [B,4,H,W] = (rgb / 255 as an IEEE division, prev_mask): the operand of
+ * vpu_forward, from 3 uploaded bytes per pixel instead of 12. */
+int vpu_image_from_u8(const uint8_t* rgb_nhwc, const float* prev_mask, float* image4, int B, int H, int W, void* stream);
 /* measurement only: CTA 0 of the following global-attention launches logs (event << 56 | clock64) per role into
  * dev_buf[4][cap] (uint64; roles: TMA thread, MMA thread, softmax warpgroup 0 / 1); NULL switches it off */
 int vpu_debug_attention_trace(void* dev_buf, int cap);

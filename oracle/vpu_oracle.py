@@ -35,8 +35,8 @@ def disk_maps(points, rows, cols, norm_radius=5):
     pts = points.reshape(-1, points.shape[2])
     xy = pts[:, :2]
     invalid = xy.max(dim=1)[0] < 0                                  # ops.py:352
-    rr = torch.arange(rows, dtype=torch.float32).view(1, rows, 1)
-    cc = torch.arange(cols, dtype=torch.float32).view(1, 1, cols)
+    rr = torch.arange(rows, dtype=torch.float32, device=points.device).view(1, rows, 1)
+    cc = torch.arange(cols, dtype=torch.float32, device=points.device).view(1, 1, cols)
     # ops.py:356-365: coords.add_(-points) is an in-place add on a float32 grid: the difference is
     # formed in the promoted dtype (float64 for float64 clicks) and rounded to float32 once;
     # then squared and summed in float32.
@@ -357,7 +357,7 @@ def pos2d(d_model, height, width):
 def dma(sd, cfg, q0, x, taps=None):
     """transformer.py:323-384 + 432-463 (TwoWayTransformer, return_intermediate=True)."""
     H = cfg.dma_heads
-    key_pe = pos2d(cfg.embed_dim, cfg.grid, cfg.grid)
+    key_pe = pos2d(cfg.embed_dim, cfg.grid, cfg.grid).to(x.device)
     queries, keys = q0, x
     inter = []
     for j in range(cfg.dma_depth):
@@ -457,10 +457,14 @@ def head(sd, cfg, feats, q_out, taps=None):
 
 
 def forward(sd, cfg, image4, points, prompts=None, as_prompt_type=0, taps=None, rng=random,
-            want_aux=True):
-    """is_vpu_model.py:422-438.  image4 [B,4,H,W] fp32, points [B,2n,3]."""
-    mean = torch.tensor(cfg.norm_mean, dtype=torch.float32).view(1, 3, 1, 1)
-    std = torch.tensor(cfg.norm_std, dtype=torch.float32).view(1, 3, 1, 1)
+            want_aux=True, ppue_rows=None):
+    """is_vpu_model.py:422-438.  image4 [B,4,H,W] fp32, points [B,2n,3].
+
+    `ppue_rows` (optional, [B,48,899]): PPuE rows computed beforehand by `ppue` -- used by bench.py's eager-GPU bar, which
+    runs this same restatement with tensors on a CUDA device and keeps the reference's per-point host loops (ops.py:80-104)
+    out of its timed region; the CPU oracle path never passes it."""
+    mean = torch.tensor(cfg.norm_mean, dtype=torch.float32, device=image4.device).view(1, 3, 1, 1)
+    std = torch.tensor(cfg.norm_std, dtype=torch.float32, device=image4.device).view(1, 3, 1, 1)
     img = (image4[:, :3].clone() - mean) / std                       # ops.py:403-407
     cf = coord_features(image4, points, prompts, as_prompt_type, cfg.norm_radius)
     if taps is not None:
@@ -469,7 +473,8 @@ def forward(sd, cfg, image4, points, prompts=None, as_prompt_type=0, taps=None, 
     if taps is not None:
         taps["backbone_features"] = x
     pv_points = prompts[0] if as_prompt_type != 0 else points         # is_vpu_model.py:396-397
-    rows = ppue(pv_points, prompts, as_prompt_type, cfg.img_size, cfg.num_max_points, rng)
+    rows = ppue_rows if ppue_rows is not None else \
+        ppue(pv_points, prompts, as_prompt_type, cfg.img_size, cfg.num_max_points, rng)
     if taps is not None:
         taps["ppue"] = rows
     feats, q_out = neck(sd, cfg, x, rows, taps)

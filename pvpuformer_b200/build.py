@@ -44,17 +44,30 @@ def is_current():
         return f.read().strip() == _digest()
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link the shared library.  Returns the library path."""
+def build(force=False, verbose=False, debug=False):
+    """Compile every .cu for sm_100a and link the shared library.  Returns the library path.
+
+    debug=True builds libvpuformer_b200_debug.so with -DVPU_DEBUG -DVPU_ATTN_DEBUG next to the shipped library: only that build
+    reads the development knobs (VPU_GEMM_IMPL, VPU_ATTN_TC, VPU_ATTN_NARROW, VPU_PDL, VPU_GEMM_*, VPU_ATTN_ABLATE) and compiles
+    the clock64 trace points; load it with VPU_LIB_PATH (tools/ab_bench.sh)."""
+    if debug:
+        return _build_to(os.path.join(HERE, "libvpuformer_b200_debug.so"), os.path.join(HERE, "build_debug"),
+                         ["-DVPU_DEBUG", "-DVPU_ATTN_DEBUG"], verbose)
     if not force and is_current():
         return LIB
+    _build_to(LIB, os.path.join(HERE, "build"), [], verbose)
+    with open(STAMP, "w") as f:
+        f.write(_digest())
+    return LIB
+
+
+def _build_to(lib_path, objdir, extra, verbose):
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + [f for f in FLAGS if f != "--use_fast_math=false"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + [f for f in FLAGS if f != "--use_fast_math=false"] + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -66,14 +79,12 @@ def build(force=False, verbose=False):
         if verbose:
             print(out)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)
-    with open(STAMP, "w") as f:
-        f.write(_digest())
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

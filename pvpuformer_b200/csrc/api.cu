@@ -709,7 +709,7 @@ int vpu_create(vpu_handle* out, const vpu_dims* dims) {
     VPU_REQUIRE((d.img_size / d.patch) % (224 / d.patch) == 0 && (d.img_size / d.patch) % 2 == 0, "grid must tile into 224-px windows");
     vpu_context* h = new vpu_context();
     h->d = d;
-    const char* impl = getenv("VPU_GEMM_IMPL");
+    const char* impl = vpu_debug_env("VPU_GEMM_IMPL");
     h->gemm_impl = (impl && impl[0] == '1') ? 1 : 0;
     // click Gaussian table: the reference's float32 formula (ops.py:51-61), sigma = 3, peak + 1
     const int r = 9;
@@ -903,6 +903,10 @@ int vpu_session_prepare(const vpu_session_state* st, const int32_t* active, int 
 int vpu_session_finish(const vpu_session_state* st, const int32_t* active, int A, const float* logits, void* stream) {
     VPU_REQUIRE(st, "vpu_session_finish: null state");
     return session_finish_launch(to_session(st), active, A, logits, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_image_from_u8(const uint8_t* rgb_nhwc, const float* prev_mask, float* image4, int B, int H, int W, void* stream) {
+    return image_from_u8_launch(rgb_nhwc, prev_mask, image4, B, H, W, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vpu_debug_attention_trace(void* dev_buf, int cap) {

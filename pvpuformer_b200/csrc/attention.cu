@@ -249,7 +249,7 @@ static int launch_att_t(const AttnArgs& a, cudaStream_t stream) {
 }
 template <int D>
 static int launch_att(const AttnArgs& a, cudaStream_t stream) {
-    static const bool narrow = [] { const char* e = getenv("VPU_ATTN_NARROW"); return !(e && e[0] == '0'); }();
+    static const bool narrow = [] { const char* e = vpu_debug_env("VPU_ATTN_NARROW"); return !(e && e[0] == '0'); }();
     const bool q48 = narrow && a.Sq <= 48, k48 = narrow && a.Sk <= 48;
     if (q48 && k48) return launch_att_t<D, 48, 48>(a, stream);
     if (q48) return launch_att_t<D, 48, 64>(a, stream);
@@ -263,7 +263,7 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
                     a.koff % 8 == 0 && a.voff % 8 == 0,
                 "attention strides/offsets must be multiples of 8 elements");
     VPU_REQUIRE(a.nprob <= 65535 && a.heads <= 65535, "attention grid too large");
-    static const bool use_tc = [] { const char* e = getenv("VPU_ATTN_TC"); return !(e && e[0] == '0'); }();
+    static const bool use_tc = [] { const char* e = vpu_debug_env("VPU_ATTN_TC"); return !(e && e[0] == '0'); }();
     if (use_tc && window_attention_tc_supported(a, head_dim)) return window_attention_tc_launch(a, stream);
     if (use_tc && window_attention_tc80_supported(a, head_dim)) return window_attention_tc80_launch(a, stream);
     if (use_tc && global_attention_tc80_supported(a, head_dim)) return global_attention_tc80_launch(a, stream);

@@ -1597,7 +1597,7 @@ int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
     g.ntiles = (a.Sq + G_QT - 1) / G_QT; g.npairs = (g.ntiles + 1) / 2;
     g.nunits = a.nprob * a.heads * g.npairs;
     g.qcol = a.qoff; g.kcol = a.koff; g.vcol = a.voff; g.scale_log2 = a.scale_log2;
-    static const int ablate = [] { const char* e = getenv("VPU_ATTN_ABLATE"); return e ? atoi(e) : 0; }();
+    static const int ablate = [] { const char* e = vpu_debug_env("VPU_ATTN_ABLATE"); return e ? atoi(e) : 0; }();
     g.ablate = ablate;
     g.trace = g_trace; g.trace_cap = g_trace_cap;
     const int ctas = g.nunits < g_sms ? g.nunits : g_sms;

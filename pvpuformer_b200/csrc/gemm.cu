@@ -37,7 +37,7 @@ const char* last_error() { return g_err; }
 static thread_local bool g_pdl_auto = false;
 void pdl_set_auto(bool on) { g_pdl_auto = on; }
 bool pdl_enabled() {
-    static const int forced = [] { const char* e = getenv("VPU_PDL"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    static const int forced = [] { const char* e = vpu_debug_env("VPU_PDL"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     return forced >= 0 ? forced == 1 : g_pdl_auto;
 }
 
@@ -929,12 +929,12 @@ int gemm_init() {
                 prop.major, prop.minor);
     g_num_sms = prop.multiProcessorCount;
     if (int rc = set_smem_attrs()) return rc;
-    const char* two = getenv("VPU_GEMM_2CTA");
+    const char* two = vpu_debug_env("VPU_GEMM_2CTA");
     g_use_2cta = !(two && two[0] == '0');
-    if (const char* st = getenv("VPU_GEMM_STAGES")) g_stages = atoi(st);
-    if (const char* cl = getenv("VPU_GEMM_CLUSTER")) g_cluster = atoi(cl) == 4 ? 4 : 2;
-    if (const char* ab = getenv("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
-    if (const char* rg = getenv("VPU_GEMM_RAGGED256")) g_ragged256 = rg[0] != '0';
+    if (const char* st = vpu_debug_env("VPU_GEMM_STAGES")) g_stages = atoi(st);
+    if (const char* cl = vpu_debug_env("VPU_GEMM_CLUSTER")) g_cluster = atoi(cl) == 4 ? 4 : 2;
+    if (const char* ab = vpu_debug_env("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
+    if (const char* rg = vpu_debug_env("VPU_GEMM_RAGGED256")) g_ragged256 = rg[0] != '0';
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }

@@ -31,7 +31,8 @@ constexpr int ROW_THREADS = 256;
 __device__ __forceinline__ bool err_at(const int8_t* gt, const uint8_t* pred, size_t i, bool fn) {
     const int g = gt[i];
     const bool p = pred[i] != 0;
-    return fn ? (g == 1 && !p) : (g == 0 && p);
+    // clicker.py:31-32: fn = (gt == 1) & !pred ; fp = !(gt == 1) & pred, both restricted to gt != -1 (any other label is background)
+    return fn ? (g == 1 && !p) : (g != 1 && g != -1 && p);
 }
 
 __global__ void __launch_bounds__(128) noc_cols_kernel(const int8_t* __restrict__ gt, const uint8_t* __restrict__ pred, int S, int H,

@@ -20,6 +20,7 @@ struct SessionState {
 
 int session_prepare_launch(const SessionState& st, const int32_t* active, int A, const int32_t* new_clicks, float* net_image,
                            double* net_points, cudaStream_t stream);
+int image_from_u8_launch(const uint8_t* rgb_nhwc, const float* prev, float* image4, int B, int H, int W, cudaStream_t stream);
 int session_finish_launch(const SessionState& st, const int32_t* active, int A, const float* logits, cudaStream_t stream);
 
 }  // namespace vpu

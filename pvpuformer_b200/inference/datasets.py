@@ -30,3 +30,21 @@ class SyntheticEllipseDataset:
         yy, xx = self._grid
         mask = ((((yy - cy) / a) ** 2 + ((xx - cx) / b) ** 2) <= 1).astype(np.int32)
         return Sample(image, mask)
+
+
+class MaterialisedShard:
+    """A rank's block of a dataset generated up front (decoded images in host memory): keeps sample generation out of a timed
+    evaluation loop.  Indexable like the dataset itself; only indices of this rank's contiguous shard are held."""
+
+    def __init__(self, ds, rank=0, world=1):
+        from .evaluation import shard_range
+        self.ds = ds
+        self.name = getattr(ds, "name", "dataset")
+        a, b = shard_range(len(ds), rank, world)
+        self.cache = {i: ds.get_sample(i) for i in range(a, b)}
+
+    def __len__(self):
+        return len(self.ds)
+
+    def get_sample(self, index):
+        return self.cache[index]

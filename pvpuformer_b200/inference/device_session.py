@@ -48,11 +48,16 @@ class DeviceClickSessions:
         self.n_half = int(max_clicks)
         S = self.S
         im = np.stack([np.asarray(i) for i in images])                       # [S,H,W,3]
-        t = torch.from_numpy(np.ascontiguousarray(im)).to(device).permute(0, 3, 1, 2)
-        # predictor._to_tensor (ToTensor): x / 255 as a true IEEE division -- dividing by a device tensor, because torch's CUDA
-        # division by a Python scalar multiplies by the reciprocal (1 ulp off the host result for some x)
-        self.images = (t.float() / torch.full((), 255.0, device=device) if im.dtype == np.uint8 else t.float()).contiguous()
-        self.gt = torch.from_numpy(np.stack(gts).astype(np.int8)).to(device)
+        t = torch.from_numpy(np.ascontiguousarray(im)).to(device)
+        if im.dtype == np.uint8:
+            # predictor._to_tensor (ToTensor): x / 255 as a true IEEE division, on the device (vpu_image_from_u8); torch's CUDA
+            # division by a Python scalar would multiply by the reciprocal (1 ulp off the host result for some x)
+            from .. import ops
+            self.images = ops.image_from_u8(t)[:, :3].contiguous()
+        else:
+            self.images = t.permute(0, 3, 1, 2).float().contiguous()
+        from .evaluation import gt_labels_int8
+        self.gt = torch.from_numpy(gt_labels_int8(gts)).to(device)
         self.prev_probs = torch.zeros(S, H, W, dtype=torch.float32, device=device)
         self.pred = torch.zeros(S, H, W, dtype=torch.uint8, device=device)
         self.not_clicked = torch.ones(S, H, W, dtype=torch.uint8, device=device)

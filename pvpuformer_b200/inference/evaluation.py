@@ -116,8 +116,13 @@ def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clic
             for i in chunk:
                 image, gt = samples[i]
                 p = predictor_factory(net, device)
-                if p.cascade_step > 1:
-                    raise NotImplementedError("lock-step evaluation supports cascade_step <= 1")
+                if p.cascade_step > 1 or p.cascade_adaptive:
+                    raise NotImplementedError("lock-step evaluation supports cascade_step <= 1, cascade_adaptive=False")
+                if p.zoom_in is not None and p.zoom_in.skip_clicks >= 0:
+                    # the serial path re-runs a click when ZoomIn.check_possible_recalculation() fires (base.py:185-186); that
+                    # only happens while _object_roi is unset, i.e. with skip_clicks >= 0 -- not reproduced in lock-step
+                    raise NotImplementedError("lock-step evaluation needs ZoomIn(skip_clicks=-1) (the VPU evaluation's setting) "
+                                              "or no zoom-in; got skip_clicks=%d" % p.zoom_in.skip_clicks)
                 p.set_input_image(image)
                 sess[i] = dict(pred=p, clicker=Clicker(gt_mask=gt), gt=gt, mask=np.zeros_like(gt), ious=[])
             dc = _DeviceClickerBatch([sess[i]["gt"] for i in chunk], device) if device_clicker else None
@@ -173,6 +178,17 @@ def evaluate_lockstep(samples, net, device, max_iou_thr, pred_thr=0.49, min_clic
     return results
 
 
+def gt_labels_int8(gts):
+    """Ground-truth masks -> int8 [S,H,W] for the device clicker, whose contract is 1 = object, -1 = ignore, anything else =
+    background (clicker.py:31-32, utils.py:80-87).  A plain astype(int8) would wrap 255 to -1 and silently turn an ordinary
+    label into `ignore`, so labels outside {-1, 0, 1} are mapped to 0 explicitly."""
+    a = np.stack([np.asarray(g) for g in gts])
+    out = np.zeros(a.shape, dtype=np.int8)
+    out[a == 1] = 1
+    out[a == -1] = -1
+    return out
+
+
 class _DeviceClickerBatch:
     """Ground truth / prediction / not-clicked maps of one micro-batch on the device + one clicker call per click."""
 
@@ -185,7 +201,7 @@ class _DeviceClickerBatch:
         if gts[0].shape[0] * gts[0].shape[1] < 20000:
             raise ValueError("device_clicker is bit-exact with the cv2 clicker only for masks of >= 2e4 pixels (csrc/noc.cu); "
                              "use device_clicker=False for %s" % (gts[0].shape,))
-        self.gt = torch.from_numpy(np.stack([np.asarray(g).astype(np.int8) for g in gts])).to(device)
+        self.gt = torch.from_numpy(gt_labels_int8(gts)).to(device)
         self.pred = torch.zeros(self.gt.shape, dtype=torch.uint8, device=device)
         self.not_clicked = torch.ones(self.gt.shape, dtype=torch.uint8, device=device)
         self.workspace = None
@@ -228,32 +244,40 @@ def iou_table(all_ious, max_clicks):
     return t
 
 
-def gather_iou_tables(local_table, n_total, group=None, device=None):
-    """all_gather of the per-rank [n_local, max_clicks] tables -> [n_total, max_clicks] on every rank (rank order ==
-    image order because shards are contiguous).  The only collective of the sharded NoC loop."""
+def gather_iou_tables(local_table, n_total=None, group=None, device=None):
+    """all_gather of the per-rank [rows_local, max_clicks] tables -> [sum of rows, max_clicks] on every rank (rank order ==
+    image order because shards are contiguous).  A row is one (image, object) pair, so ranks first exchange their row
+    counts (images with several objects make them differ from the image shard sizes) and the tables are padded to the
+    largest one.  The only data collective of the sharded NoC loop.  `n_total`, if given, is checked against the result."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return local_table
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world = dist.get_world_size(group)
     max_clicks = local_table.shape[1]
-    cap = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    cnt = torch.tensor([local_table.shape[0]], dtype=torch.int64)
+    if device is not None:
+        cnt = cnt.to(device)
+    counts = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
     buf = torch.full((cap, max_clicks), float("nan"), dtype=torch.float32)
     buf[:local_table.shape[0]] = torch.from_numpy(local_table)
     if device is not None:
         buf = buf.to(device)
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
-    parts = []
-    for r in range(world):
-        a, b = shard_range(n_total, r, world)
-        parts.append(out[r][:b - a].cpu().numpy())
-    return np.concatenate(parts, axis=0)
+    table = np.concatenate([out[r][:counts[r]].cpu().numpy() for r in range(world)], axis=0)
+    if n_total is not None and table.shape[0] != n_total:
+        raise RuntimeError("gathered %d IoU rows, expected %d" % (table.shape[0], n_total))
+    return table
 
 
 def evaluate_sharded(dataset, net, device, rank, world, max_iou_thr, max_clicks=20, micro_batch=32, group=None,
                      gather_device=None, **kwargs):
-    """Rank `rank` evaluates images [start, stop) in lock-step micro-batches; returns the full [n, max_clicks] IoU
-    table (after the all_gather) and the local wall-clock seconds of the loop."""
+    """Rank `rank` evaluates images [start, stop) in lock-step micro-batches; returns the full [objects, max_clicks] IoU
+    table (one row per (image, object) pair in dataset order, after the all_gather) and the local wall-clock seconds of
+    the loop."""
     start, stop = shard_range(len(dataset), rank, world)
     samples = []
     for index in range(start, stop):
@@ -265,5 +289,5 @@ def evaluate_sharded(dataset, net, device, rank, world, max_iou_thr, max_clicks=
     ious = evaluate_lockstep(samples, net, device, max_iou_thr, max_clicks=max_clicks, micro_batch=micro_batch, stats=stats,
                              **kwargs)
     elapsed = time() - t0
-    table = gather_iou_tables(iou_table(ious, max_clicks), len(dataset), group=group, device=gather_device)
+    table = gather_iou_tables(iou_table(ious, max_clicks), group=group, device=gather_device)
     return table, elapsed, stats

@@ -8,7 +8,9 @@ exactly prepare -> net -> finish.
 
 Prompt simulation: the reference rebuilds box and scribble prompts on the host at every click
 (engine/trainer.py:703-768) even though `as_prompt_type == 0` never reads them.  Here click-only prediction passes
-prompts=None; for prompt types 1/2 `prompt_fn(prev_mask_roi, gt_mask_roi, points_nd) -> prompts` is called, by default
+prompts=None -- which also means the host `random` / numpy RNG draws of those unused simulations are NOT consumed for
+type 0: a seeded run that mixes prompt types per click sees a different RNG stream than the reference from the first
+type-0 click on (runs of a single type, what evaluate_vpumodel.py does, are unaffected); for prompt types 1/2 `prompt_fn(prev_mask_roi, gt_mask_roi, points_nd) -> prompts` is called, by default
 the restated simulators of inference/prompts.py (`eval_prompt_fn`).
 """
 import numpy as np
@@ -146,6 +148,10 @@ class BasePredictor:
                         return prediction, prompts_nd
                 prev_mask = prediction
             return prediction, prompts_nd
+        if not as_multi_prompts:
+            # the reference's as_multi_prompts=False branch (base.py:153-163, trainer.get_next_promts_inference) rewrites points_nd
+            # from simulated prompts and calls net(image, points) without them: a different prediction, not part of this path
+            raise NotImplementedError("as_multi_prompts=False (_get_vqu_prediction_points, base.py:153-163) is outside the B200 path")
         image_nd, points_nd, prompts_nd = self.prepare_inputs(clicker, prev_mask, gt_mask, as_prompt_type)
         if prompts_nd is None:
             logits = self.net(image_nd, points_nd)["instances"]

@@ -66,6 +66,7 @@ SIGNATURES = {
     "vpu_raster_prompts": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vpu_session_prepare": (c_int, [POINTER(VpuSessionState), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpu_session_finish": (c_int, [POINTER(VpuSessionState), c_void_p, c_int, c_void_p, c_void_p]),
+    "vpu_image_from_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vpu_debug_attention_trace": (c_int, [c_void_p, c_int]),
     "vpu_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),

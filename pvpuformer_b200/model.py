@@ -161,12 +161,33 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
             self._ws = {}
 
     def workspace(self, B, device):
-        if B not in self._ws:
-            nbytes = L.load().vpu_workspace_bytes(self._handle, B)
-            self._ws = {B: torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)}   # keep one size cached
-        ws = self._ws[B]
+        """One buffer, sized for the largest batch seen so far and reused by every smaller one (the static plan of
+        vpu_workspace_bytes(B) always starts at offset 0): a NoC loop whose active set shrinks click by click never
+        re-allocates.  Growing replaces the buffer; the old one is returned to torch's caching allocator, which keeps it
+        alive until the work already queued on it has run."""
+        need = L.load().vpu_workspace_bytes(self._handle, B)
+        ws = self._ws.get("buf")
+        if ws is None or ws.numel() < need + 1024 or ws.device != device:
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
+            self._ws = {"buf": ws}
         off = (-ws.data_ptr()) % 1024
         return ws[off:]
+
+    def _serialize_streams(self):
+        """The workspace is shared by every forward of this module: a forward issued on another stream than the previous
+        one first waits for it (device-side event wait, no host sync), so two pipelines over one model cannot race on the
+        activations."""
+        cur = torch.cuda.current_stream()
+        last = getattr(self, "_last_use", None)
+        if last is not None and last[0] != cur.cuda_stream:
+            cur.wait_event(last[1])
+        return cur
+
+    def _mark_use(self, stream):
+        last = getattr(self, "_last_use", None)
+        ev = last[1] if last is not None else torch.cuda.Event()
+        ev.record(stream)
+        self._last_use = (stream.cuda_stream, ev)
 
     def tap(self, name, B, dtype, shape):
         """View of a named intermediate of the LAST forward with batch B (parity tests)."""
@@ -247,8 +268,10 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
         want_aux = self.with_aux_output and self.want_aux
         aux = torch.empty(B, self.cfg.num_queries, s, s, dtype=torch.float32, device=device) if want_aux else None
         ws = self.workspace(B, device)
+        stream = self._serialize_streams()
         L.check(L.load().vpu_forward(self._handle, L.ptr(image), ctypes.byref(pr), B, L.ptr(inst), L.ptr(aux),
                                      L.ptr(ws), ws.numel(), L.current_stream()))
+        self._mark_use(stream)
         self._keepalive = (keep, image)     # inputs must outlive the asynchronous kernels
         return {"instances": inst, "instances_aux": aux}
 

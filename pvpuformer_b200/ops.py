@@ -104,3 +104,18 @@ def raster_prompts(as_prompt_type, boxes, scribbles, n, B, size=448, device=None
                                         L.ptr(scribbles) if as_prompt_type == 2 else None, S, n, B, size, L.ptr(planes),
                                         L.current_stream()))
     return planes
+
+
+def image_from_u8(rgb_nhwc, prev_mask=None, out=None):
+    """ToTensor + cat(prev mask) of the predictor for a batch on the device (csrc/session.cu; reference
+    inference/predictors/base.py:30,45,113-115): uint8 cuda [B,H,W,3] (+ fp32 [B,H,W] or [B,1,H,W]) -> fp32 [B,4,H,W]."""
+    assert rgb_nhwc.is_cuda and rgb_nhwc.dtype == torch.uint8 and rgb_nhwc.dim() == 4 and rgb_nhwc.shape[3] == 3
+    rgb_nhwc = rgb_nhwc.contiguous()
+    B, H, W, _ = rgb_nhwc.shape
+    if prev_mask is not None:
+        assert prev_mask.is_cuda and prev_mask.dtype == torch.float32 and prev_mask.numel() == B * H * W
+        prev_mask = prev_mask.contiguous()
+    if out is None:
+        out = torch.empty(B, 4, H, W, dtype=torch.float32, device=rgb_nhwc.device)
+    L.check(L.load().vpu_image_from_u8(L.ptr(rgb_nhwc), L.ptr(prev_mask), L.ptr(out), B, H, W, L.current_stream()))
+    return out

@@ -83,7 +83,8 @@ def pack_weights(sd, cfg, device):
         F32(dst + ".s", wq.float().sum(dim=1))                                # row sums of the ROUNDED W': consistent with the MMA
         F32(dst + ".b", w @ f[ln + ".bias"] + f[src + ".bias"])
 
-    ln_fold = os.environ.get("VPU_LN_FOLD", "1") != "0"
+    # development knob, honoured only together with the -DVPU_DEBUG library (build.py --debug): the shipped path always folds
+    ln_fold = not (os.environ.get("VPU_LN_FOLD") == "0" and os.environ.get("VPU_LIB_PATH", "").endswith("_debug.so"))
     scalars["vit.ln_fold"] = 1.0 if ln_fold else 0.0
     if ln_fold:
         F32("pe.zero_b", torch.zeros(C, device=device))

@@ -213,6 +213,79 @@ def test_sharded_loop_world_size_2_gloo():
     assert sum(f for _, _, f in got) == 2 * int(np.isfinite(serial).sum())
 
 
+class _MultiObjectDataset:
+    """Image i holds 1 + (i % 3) objects (labels 1..k): rows of the IoU table are (image, object) pairs, not images."""
+
+    def __init__(self, n):
+        self.base = SyntheticEllipseDataset(n)
+
+    def __len__(self):
+        return len(self.base)
+
+    def get_sample(self, index):
+        s = self.base.get_sample(index)
+        k = 1 + index % 3
+        m = np.zeros_like(s._mask)
+        H = m.shape[0]
+        for o in range(k):                                 # k horizontal bands of the ellipse -> k objects
+            band = slice(o * H // k, (o + 1) * H // k)
+            m[band][s._mask[band] == 1] = o + 1
+        s._mask = m
+        s.objects_ids = [o + 1 for o in range(k) if (m == o + 1).sum() > 0]
+        return s
+
+
+def _worker_multi(rank, world, port, n_images, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    table, _, _ = evaluate_sharded(_MultiObjectDataset(n_images), FakeNet(), "cpu", rank, world, 0.55, max_clicks=3, micro_batch=2)
+    out_q.put((rank, table))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_loop_multi_object_rows_world_size_2_gloo():
+    """Ranks hold different numbers of (image, object) rows (here 3 + 2 images -> 6 + 3 rows... whatever the dataset gives): the
+    gathered table must have one row per pair, in dataset order, on every rank."""
+    n_images, world = 5, 2
+    ds = _MultiObjectDataset(n_images)
+    samples = []
+    for i in range(n_images):
+        s = ds.get_sample(i)
+        samples += [(s.image, s.gt_mask(o)) for o in s.objects_ids]
+    assert len(samples) > n_images
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_multi, args=(r, world, port, n_images, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    serial = iou_table(evaluate_lockstep(samples, FakeNet(), "cpu", 0.55, max_clicks=3, micro_batch=8), 3)
+    for _, table in got:
+        assert table.shape == serial.shape
+        assert np.array_equal(np.nan_to_num(table, nan=-1), np.nan_to_num(serial, nan=-1))
+
+
+def test_gt_labels_for_device_clicker():
+    from pvpuformer_b200.inference.evaluation import gt_labels_int8
+    g = np.array([[0, 1, 255, -1, 2]], dtype=np.int32)
+    assert gt_labels_int8([g]).tolist() == [[[0, 1, 0, -1, 0]]]
+
+
+def test_lockstep_refuses_recalculating_zoom_in():
+    from pvpuformer_b200.inference.predictor import get_predictor
+    factory = lambda net, dev: get_predictor(net, "NoBRS", dev, zoom_in_params={"skip_clicks": 1, "target_size": (448, 448)})
+    with pytest.raises(NotImplementedError):
+        evaluate_lockstep(_samples(1), FakeNet(), "cpu", 0.9, max_clicks=2, predictor_factory=factory)
+
+
 def test_gather_without_process_group_is_identity():
     t = np.zeros((3, 4), np.float32)
     assert gather_iou_tables(t, 3) is t
