@@ -93,6 +93,14 @@ def train12(model):
 def main():
     os.makedirs(OUT, exist_ok=True)
     rh.import_reference()
+    if "--only-large-huge" not in sys.argv:
+        base_cases()
+    large_huge_cases()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def base_cases():
     from isegm.engine.trainer import get_next_promts
 
     cfg = make_config("vit_base")
@@ -129,18 +137,19 @@ def main():
     train12(model)
     del model
 
+
+
+def large_huge_cases():
+    """ViT-L / ViT-H clicks (B=2): the full fixture set of the ViT-B cases (PPuE rows, disks, low-res and full-res logits, aux
+    selection), so that the L/H parity tests carry the same gates as the ViT-B ones."""
     for arch in ("vit_large", "vit_huge"):
         cfg = make_config(arch)
         model = rh.build_reference_model(arch)
         model.load_state_dict(synthetic_state_dict(cfg, 0), strict=True)
         image4 = cases.images(2, seed=1)
         out, taps = run_reference(model, image4, cases.CLICKS_A)
-        d = pack(out, taps)
-        keep = {k: d[k] for k in ("seg_lowres", "aux_lowres_sel", "instances_row100", "backbone_slice", "q_out_slice")}
-        np.savez_compressed(os.path.join(OUT, "%s_clicks.npz" % arch), **keep)
+        np.savez_compressed(os.path.join(OUT, "%s_clicks.npz" % arch), **pack(out, taps))
         del model
-    for f in sorted(os.listdir(OUT)):
-        print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
 if __name__ == "__main__":

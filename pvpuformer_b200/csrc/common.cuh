@@ -11,14 +11,14 @@ namespace vpu {
 
 // ---- host-side error plumbing (thread-local message read back by vpu_last_error) -----------
 void set_error(const char* fmt, ...);
-void count_launch(int n = 1);
+void count_launch(int n = 1);        // every kernel launch of this library is counted (vpu_launch_count)
 // Development knobs (A/B variants of kernels, ablations) are read from the environment only in -DVPU_DEBUG builds
 // (python -m pvpuformer_b200.build --debug); the shipped library has one path per operation and ignores them.
 #ifdef VPU_DEBUG
 inline const char* vpu_debug_env(const char* name) { return getenv(name); }
 #else
 inline const char* vpu_debug_env(const char*) { return nullptr; }
-#endif        // every kernel launch of this library is counted (vpu_launch_count)
+#endif
 unsigned long long launch_count();
 #define VPU_CHECK_CUDA(expr)                                                              \
     do {                                                                                  \

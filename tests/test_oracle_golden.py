@@ -77,6 +77,25 @@ def test_oracle_matches_reference_golden_large_huge(arch):
     assert np.abs(taps["aux_lowres"][:, [0, 1, 23, 24, 25, 47]].numpy() - g["aux_lowres_sel"]).max() < 1e-4
 
 
+def test_oracle_matches_reference_golden_config3_sample_of_each_prompt_type():
+    """BASELINE.json configs[2] fixture (ViT-L, batch 32 = 11 clicks + 11 boxes + 10 scribbles, oracle/make_golden_config3.py): the
+    oracle on the first two samples of every sub-batch against the unmodified reference's stride-8 logits."""
+    from oracle.make_golden_config3 import SPLIT, inputs
+    cfg = make_config("vit_large")
+    g = gu.load("vit_large_config3")
+    image4, pts, _ = inputs()
+    for t, a, b in SPLIT:
+        prompts = None
+        if t != 0:
+            prompts = (torch.from_numpy(g["t%d_prompt_points" % t])[:2], torch.from_numpy(g["t%d_boxes" % t])[:2],
+                       [g["t%d_scribbles" % t][:2], g["t%d_rects" % t][:2]])
+        gu.seed_scribble()
+        with torch.no_grad():
+            out = vo.forward(_sd("vit_large"), cfg, image4[a:a + 2], pts[a:a + 2], prompts, t)
+        assert np.abs(out["instances"][:, :, ::8, ::8].numpy() - g["instances_s8"][a:a + 2]).max() < 1e-4, t
+        assert np.abs(out["instances_aux"][:, [0, 24], ::16, ::16].numpy() - g["aux_s16_sel"][a:a + 2]).max() < 1e-4, t
+
+
 def test_ppue_quirks():
     """Reference quirks: corner-drop, trunc toward zero, '>' bounds, peak 2.0."""
     vx, vy = vo.ppue_click_row([224.9, 10.2])
