@@ -20,6 +20,7 @@
 #include <unordered_map>
 
 #include "attention.cuh"
+#include "tc_attn.cuh"
 
 namespace vpu {
 
@@ -62,42 +63,6 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU; arguments are <= 0 here, results in (0, 1]
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 // 16 fp32 accumulators * inv -> 16 bf16 -> one 32-byte global store (STG.256).  An epilogue thread owns one output row, so
 // every store instruction of a warp touches 32 different lines and the L1 store path charges per line touched, not per
 // byte (clock64 trace, round 1i: ten 16-byte stores per thread took 2300 clk per tile): half as many instructions, half the cost.
@@ -108,24 +73,6 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const uint32_t*
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// MN-major 128B-swizzled operand (V: rows = keys (K), 64 head-dim elements = one 128-byte row):
-// 8-row swizzle atoms 1024 B apart along K (SBO); a single 64-element block along N, so LBO is unused.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
-}
-
 static unsigned long long* g_trace = nullptr;     // vpu_debug_attention_trace
 static int g_trace_cap = 0;
 
@@ -478,18 +425,6 @@ constexpr int G_P_COL = 112, G_O_COL = 192;
 static_assert(G_SMEM_BYTES <= 232448 && SMEM_BYTES <= 232448, "dynamic shared memory limit of sm_100");
 constexpr int G_MMA1_WARP = 10;                      // warp 0 TMA, 1 MMA tile 0, 2-5 / 6-9 softmax tile 0 / 1, 10 MMA tile 1
 constexpr int G_THREADS = 352;
-
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
-        "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
 
 struct GlobArgs {
     __nv_bfloat16* o;
@@ -861,18 +796,6 @@ constexpr int O_MAIN_COL = 128, O_TAIL_COL = 192;
 static_assert(Q_MAIN % 1024 == 0 && Q_TILE % 1024 == 0 && KV_MAIN % 1024 == 0 && KV_BUF % 1024 == 0, "swizzle atoms must stay aligned");
 static_assert(SMEM <= 232448, "dynamic shared memory limit of sm_100");
 }  // namespace h80
-
-// 32-byte-swizzled operand part (16 bf16 columns = one 32-byte row, 8-row atoms 256 B apart); the same bits describe the
-// K-major Q / K tails and the MN-major V tail (the major-ness lives in the instruction descriptor)
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;
-    return d;
-}
 
 __global__ void __launch_bounds__(THREADS, 1)
 window_attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmQt,
