@@ -187,12 +187,19 @@ struct Fwd {
     Plan plan;
     int B;
     const char* stage = "";
+    bool capturing = false; // the caller's stream is being captured into a CUDA graph: no event brackets
+    std::string label;      // per-launch label of the profile's detail mode (scalar "debug.profile_detail" = 1): the weight key
 
     // run one launch helper; in profiling mode bracket it with events and book flops / algorithmic bytes
     template <typename F> int timed(const char* kind, double flops, double bytes, F&& fn) {
-        if (!h.prof.on) return fn();
+        if (!h.prof.on || capturing) return fn();
         ProfRec r;
         r.cls = std::string(kind) + "." + stage;
+        if (!label.empty() && h.scalars.count("debug.profile_detail")) {     // "gemm.vit_window:blk.qkv.w": blocks pooled
+            std::string l = label;
+            if (l.compare(0, 3, "blk") == 0) l = "blk" + l.substr(l.find('.'));
+            r.cls += ":" + l;
+        }
         r.flops = flops; r.bytes = bytes;
         r.e0 = h.prof.get(); r.e1 = h.prof.get();
         const unsigned long long l0 = launch_count();
@@ -246,7 +253,10 @@ struct Fwd {
         }
         const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0)) +
                           (ln && ln->out ? 2.0 * M * Nn : 0.0);
-        if (int rc = timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); })) return rc;
+        label = wkey + " " + std::to_string(M) + "x" + std::to_string(Nn) + "x" + std::to_string(K);
+        const int grc = timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
+        label.clear();
+        if (grc) return grc;
         if (ln && ln->out)      // finalise the row statistics for the LayerNorm-folded GEMM that follows
             return timed("lnstats", 0, (double)M * (p.epi.ln_slots + 1) * 8.0,
                          [&] { return ln_rowstats_launch(ln->out, M, p.epi.ln_slots, h.C(), ln->eps, ln->row, s); });
@@ -260,7 +270,10 @@ struct Fwd {
         p.epi.ps_g = g; p.epi.ps_cout = cout;
         if (gn) set_gn(p.epi, *gn);
         const double by = 2.0 * ((double)M * K + 4.0 * cout * K + 4.0 * M * cout);
-        return timed("gemm", 8.0 * M * cout * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
+        label = wkey + " " + std::to_string(M) + "x" + std::to_string(4 * cout) + "x" + std::to_string(K);
+        const int grc = timed("gemm", 8.0 * M * cout * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
+        label.clear();
+        return grc;
     }
     int ln(const float* in, const std::string& key, float eps, int rows, float* of, __nv_bfloat16* ob,
            const float* pe = nullptr, __nv_bfloat16* ope = nullptr, float* rowmax = nullptr) {
@@ -320,6 +333,11 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
                 uint8_t* ws, cudaStream_t s) {
     pdl_set_auto((size_t)B * h.N() <= 16384);     // small batches are launch-latency-bound (B=2: -16 %, 8: -9 %, 16: -4 %): see pdl_enabled()
     Fwd f{h, s, ws, make_plan(h, B), B};
+    {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        VPU_CHECK_CUDA(cudaStreamIsCapturing(s, &cs));
+        f.capturing = cs != cudaStreamCaptureStatusNone;
+    }
     const int C = h.C(), N = h.N(), M = B * N, Q = h.Q(), MQ = B * Q, g = h.grid(), img = h.d.img_size;
     const int heads = h.d.num_heads, hd = C / heads;
     typedef __nv_bfloat16 bf;

@@ -1,19 +1,18 @@
-// Fused softmax(Q K^T * scale) V for every attention shape of the path, one kernel templated on
-// head_dim: ViT window (S=196/256) and global (S=784/1024) self-attention (reference
-// models_vit.py:43-56 with the 224-px window regrouping of models_vit.py:225-255 folded into the
-// row index instead of permute().contiguous()), and the three DMA attentions -- prompt
-// self-attention 48x48, tokens->image 48 x N, image->tokens N x 48 (transformer.py:499-521).
+// Dispatch of every attention shape of the path to its tcgen05 / TMEM / TMA kernel (attention_tc.cu: ViT window and global
+// self-attention, reference models_vit.py:43-56 + :225-255; attention_dma.cu: the three DMA shapes, transformer.py:499-521).
+// Q/K/V are read in place from the projection outputs (row stride + column offset), so no head split / window partition
+// copies exist.
 //
-// Round-1 implementation: flash-style online softmax on mma.sync m16n8k16 (bf16 in, fp32
-// accumulate), K/V tiles double-buffered with cp.async, scores never leave registers.
-// Q/K/V are read in place from the projection outputs (row stride + column offset), so no
-// head split / window partition copies exist.  CTA = BM / 16 warps x 16 query rows (BM, BN = 64 or 48).
+// -DVPU_DEBUG builds also compile the round-1 kernel below -- flash-style online softmax on mma.sync m16n8k16 with cp.async
+// double-buffered K/V tiles -- as the A/B baseline (VPU_ATTN_TC=0); the shipped library has no mma.sync attention and
+// rejects shapes none of the tcgen05 kernels covers.
 #include <cstdlib>
 
 #include "attention.cuh"
 
 namespace vpu {
 
+#ifdef VPU_DEBUG
 constexpr int ATT_KROW_MAX = 256;   // keys of one window (16 x 16 for ViT-H)
 
 __device__ __forceinline__ int map_row(const RowMap& rm, int prob, int s) {
@@ -257,6 +256,8 @@ static int launch_att(const AttnArgs& a, cudaStream_t stream) {
     return launch_att_t<D, 64, 64>(a, stream);
 }
 
+#endif  // VPU_DEBUG
+
 int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
     VPU_REQUIRE(a.Sq > 0 && a.Sk > 0 && a.nprob > 0 && a.heads > 0, "empty attention problem");
     VPU_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0 && a.qoff % 8 == 0 &&
@@ -268,6 +269,8 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
     if (use_tc && window_attention_tc80_supported(a, head_dim)) return window_attention_tc80_launch(a, stream);
     if (use_tc && global_attention_tc80_supported(a, head_dim)) return global_attention_tc80_launch(a, stream);
     if (use_tc && global_attention_tc_supported(a, head_dim)) return global_attention_tc_launch(a, stream);
+    if (use_tc && dma_attention_tc_supported(a, head_dim)) return dma_attention_tc_launch(a, head_dim, stream);
+#ifdef VPU_DEBUG
     switch (head_dim) {
         case 48: return launch_att<48>(a, stream);
         case 64: return launch_att<64>(a, stream);
@@ -278,6 +281,13 @@ int attention_launch(const AttnArgs& a, int head_dim, cudaStream_t stream) {
         default: VPU_REQUIRE(false, "unsupported head_dim %d (supported: 48,64,80,96,128,160)", head_dim);
     }
     return 0;
+#else
+    VPU_REQUIRE(false,
+                "attention shape Sq=%d Sk=%d head_dim=%d heads=%d window=%d has no tcgen05 kernel (ViT window 14x14 d=64 / 16x16 d=80, "
+                "global S %% 112 (d=64) or S %% 128 (d=80), DMA: 48 keys, or <= 128 queries over S %% 112 / S %% 64 keys)",
+                a.Sq, a.Sk, head_dim, a.heads, a.qmap.mode == 1 ? a.qmap.win : 0);
+    return 1;
+#endif
 }
 
 }  // namespace vpu

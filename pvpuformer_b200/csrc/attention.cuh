@@ -40,6 +40,10 @@ int global_attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
 // same for head_dim 80, S a multiple of 64 (ViT-H; attention_tc.cu)
 bool global_attention_tc80_supported(const AttnArgs& a, int head_dim);
 int global_attention_tc80_launch(const AttnArgs& a, cudaStream_t stream);
+// tcgen05 / TMEM kernels for the Dual-cross Merging Attention shapes: 48 keys (prompt self-attention, image -> tokens) or
+// <= 128 queries of an even number of heads (tokens -> image); head_dim 48 ... 160 (attention_dma.cu)
+bool dma_attention_tc_supported(const AttnArgs& a, int head_dim);
+int dma_attention_tc_launch(const AttnArgs& a, int head_dim, cudaStream_t stream);
 // measurement only: CTA 0 of the next global-attention launches logs (event << 56 | clock64) into dev_buf[4 roles][cap]
 void attention_debug_trace(unsigned long long* dev_buf, int cap);
 

@@ -63,16 +63,6 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-// 16 fp32 accumulators * inv -> 16 bf16 -> one 32-byte global store (STG.256).  An epilogue thread owns one output row, so
-// every store instruction of a warp touches 32 different lines and the L1 store path charges per line touched, not per
-// byte (clock64 trace, round 1i: ten 16-byte stores per thread took 2300 clk per tile): half as many instructions, half the cost.
-__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const uint32_t* r, float inv) {
-    uint32_t v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
 static unsigned long long* g_trace = nullptr;     // vpu_debug_attention_trace
 static int g_trace_cap = 0;
 

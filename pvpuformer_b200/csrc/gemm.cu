@@ -758,8 +758,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+#ifdef VPU_DEBUG
 // ------------------------------------------------------------------------------------------
-// mma.sync cross-check kernel (debug only; never selected by the forward unless VPU_GEMM_IMPL=1)
+// mma.sync cross-check kernel (-DVPU_DEBUG builds only: impl 1 of vpu_gemm / VPU_GEMM_IMPL=1; not part of the shipped library)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gemm_mma_kernel(const __nv_bfloat16* __restrict__ A,
                                                        const __nv_bfloat16* __restrict__ W, int lda, int ldw,
@@ -817,6 +818,7 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(const __nv_bfloat16* __re
         }
     }
 }
+#endif  // VPU_DEBUG
 
 int gemm_ln_slots(int N) { return ((N + 255) / 256) * EpiWarps<EK_F32_RES_LNOUT>::N; }
 
@@ -1084,6 +1086,9 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         return launch_tc2<256>(p, stream);
     }
     if (impl == 1) {
+#ifndef VPU_DEBUG
+        VPU_REQUIRE(false, "GEMM impl 1 (mma.sync cross-check) exists in -DVPU_DEBUG builds only");
+#else
         GemmDims d{p.M, p.N, p.K, g_stages, g_ablate};
         dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
         if (p.epi.m_per_batch > 0) VPU_REQUIRE(p.epi.m_per_batch % 64 == 0, "m_per_batch must be a multiple of 64");
@@ -1091,6 +1096,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         VPU_CHECK_CUDA(cudaGetLastError());
         count_launch();
         return 0;
+#endif
     }
     // impl 0: 2-CTA pairs whenever the shape allows it; impl 2 forces the 1-CTA kernel (A/B comparison, tests)
     if (impl == 0 && g_use_2cta && p.epi.mode != EPI_HEAD_FINAL && p.M >= 2 * BM) {

@@ -105,6 +105,10 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
         self.random_split = random_split
         self.residual = residual
         self.want_aux = True          # set False to skip the 48-channel aux upsample (NoBRS only reads 'instances')
+        # click-prompt forwards of at most this many samples (the interactive NoBRS shape: one click + flip TTA = 2) are
+        # captured once per (batch, clicks, aux) into a CUDA graph and replayed: ~185 launches become one (0 disables)
+        self.graph_max_batch = 8
+        self._graphs = {}
         for key, (shape, kind) in param_spec(self.cfg).items():
             _register(self, key, torch.zeros(shape), kind)
         pe = self.backbone.patch_embed
@@ -159,6 +163,7 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
             L.check(lib.vpu_finalize(self._handle))
             self._packed = (device, packed)
             self._ws = {}
+            self._graphs = {}
 
     def workspace(self, B, device):
         """One buffer, sized for the largest batch seen so far and reused by every smaller one (the static plan of
@@ -264,8 +269,10 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
         keep = []
         pr = self._prompt_struct(points, prompts, as_prompt_type, B, device, keep)
         s = self.cfg.img_size
-        inst = torch.empty(B, 1, s, s, dtype=torch.float32, device=device)
         want_aux = self.with_aux_output and self.want_aux
+        if as_prompt_type == 0 and 0 < B <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graph(image, keep[0], B, want_aux, device)
+        inst = torch.empty(B, 1, s, s, dtype=torch.float32, device=device)
         aux = torch.empty(B, self.cfg.num_queries, s, s, dtype=torch.float32, device=device) if want_aux else None
         ws = self.workspace(B, device)
         stream = self._serialize_streams()
@@ -274,6 +281,43 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
         self._mark_use(stream)
         self._keepalive = (keep, image)     # inputs must outlive the asynchronous kernels
         return {"instances": inst, "instances_aux": aux}
+
+    def _forward_graph(self, image, pts, B, want_aux, device):
+        """Small click-prompt batches: vpu_forward never allocates or synchronises and enqueues on one stream only, so the
+        whole forward is captured once into a CUDA graph over static input / output buffers and replayed per call (copy the
+        inputs in, replay, clone the outputs out).  The graph holds the workspace address: it is re-captured if a larger
+        batch has replaced the workspace since."""
+        s, n2 = self.cfg.img_size, pts.shape[1]
+        ws = self.workspace(B, device)
+        key = (B, n2, want_aux, device)
+        g = self._graphs.get(key)
+        stream = self._serialize_streams()
+        if g is None or g["ws_ptr"] != ws.data_ptr():
+            g = {"ws_ptr": ws.data_ptr(), "image": torch.empty_like(image), "pts": torch.empty_like(pts),
+                 "inst": torch.empty(B, 1, s, s, dtype=torch.float32, device=device),
+                 "aux": torch.empty(B, self.cfg.num_queries, s, s, dtype=torch.float32, device=device) if want_aux else None}
+            pr = L.VpuPrompts()
+            pr.points = g["pts"].data_ptr()
+            pr.n = n2 // 2
+            pr.type = 0
+            g["image"].copy_(image)
+            g["pts"].copy_(pts)
+
+            def enqueue():
+                L.check(L.load().vpu_forward(self._handle, L.ptr(g["image"]), ctypes.byref(pr), B, L.ptr(g["inst"]), L.ptr(g["aux"]),
+                                             L.ptr(ws), ws.numel(), L.current_stream()))
+            enqueue()                        # once outside the capture: tensor maps, function attributes, lazy module loading
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue()
+            g["graph"] = graph
+            self._graphs[key] = g
+        g["image"].copy_(image)
+        g["pts"].copy_(pts)
+        g["graph"].replay()
+        self._mark_use(stream)
+        return {"instances": g["inst"].clone(), "instances_aux": g["aux"].clone() if want_aux else None}
 
     @torch.no_grad()
     def ppue(self, points, prompts=None, as_prompt_type=0):

@@ -337,6 +337,35 @@ def test_full_size_batch_properties_config2():
     _rel_gates(inst[idx].cpu(), ref["instances"])
 
 
+def test_cuda_graph_replay_of_small_batches_is_bit_identical():
+    """The interactive NoBRS shape (one click + flip TTA = batch 2, reference predictors/base.py:106-151) is replayed from a
+    CUDA graph (model.graph_max_batch): same bits as the launch-by-launch forward, for fresh inputs on every replay, with
+    and without the aux output, and after a larger batch has replaced the workspace (re-capture)."""
+    from pvpuformer_b200 import synthetic
+    m, _ = _model("vit_base")
+    assert m.graph_max_batch >= 2
+    for B, aux in ((2, True), (2, False), (3, False)):
+        m.want_aux = aux
+        try:
+            for rep in range(3):
+                img = synthetic.images(B, seed=300 + rep).cuda()
+                pts = synthetic.random_clicks(B, seed=310 + rep, dtype=torch.float64).cuda()
+                out = m(img, pts)
+                gmax = m.graph_max_batch
+                m.graph_max_batch = 0
+                ref = m(img, pts)
+                m.graph_max_batch = gmax
+                assert torch.equal(out["instances"], ref["instances"]), (B, aux, rep)
+                if aux:
+                    assert torch.equal(out["instances_aux"], ref["instances_aux"])
+                else:
+                    assert out["instances_aux"] is None
+                if rep == 1:      # a larger batch grows the workspace: the graph must notice
+                    m(synthetic.images(12, seed=1).cuda(), synthetic.random_clicks(12, seed=2, dtype=torch.float64).cuda())
+        finally:
+            m.want_aux = True
+
+
 def test_error_behaviour():
     from pvpuformer_b200 import lib as L
     m, _ = _model("vit_base")

@@ -34,7 +34,7 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 2])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_plain(M, N, K, impl):
     from pvpuformer_b200 import ops
@@ -46,7 +46,7 @@ def test_gemm_plain(M, N, K, impl):
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 2])
 def test_gemm_epilogues(impl):
     from pvpuformer_b200 import ops
     M, N, K = 1568, 768, 256
@@ -79,7 +79,7 @@ def test_gemm_epilogues(impl):
     assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 2])
 def test_gemm_pixel_shuffle_matches_conv_transpose(impl):
     from pvpuformer_b200 import ops
     B, g, cin, cout = 2, 28, 256, 192
@@ -232,6 +232,36 @@ def test_attention_dma_shapes(C):
     o = ops.attention(kvq, ik, iv, N, Q, H, d_cross, B, 1 / math.sqrt(d_cross), 2 * Ci, 0, 0, out_cols=Ci)
     ref = _attn_ref(r(kvq[:, 2 * Ci:], N, d_cross), r(ik, Q, d_cross), r(iv, Q, d_cross), 1 / math.sqrt(d_cross))
     assert (o.float() - ref.transpose(1, 2).reshape(B * N, Ci)).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("C,B,amp", [(768, 70, 1.0), (768, 5, 6.0), (1024, 41, 3.0), (1280, 33, 3.0), (1280, 1, 6.0)])
+def test_attention_dma_tcgen05_many_problems(C, B, amp):
+    """The three DMA attention shapes (transformer.py:499-521) on the tcgen05 kernel (csrc/attention_dma.cu) with more
+    (image, head) units than SMs, odd batch sizes and logits of a few hundred (amp): the persistent loops wrap, the lazy
+    online-softmax rescale of the tokens -> image shape is taken, and the zero-filled query rows past 48 / past the image
+    end must not leak into a neighbouring image."""
+    from pvpuformer_b200 import ops
+    N, Q, H = 784 if C != 1280 else 1024, 48, 8
+    Ci = C // 2
+    d_self, d_cross = C // H, Ci // H
+    r = lambda t, n, d: t.reshape(B, n, H, d).transpose(1, 2)
+
+    def check(o, ref, rows, cols):
+        ref = ref.transpose(1, 2).reshape(rows, cols)
+        assert torch.isfinite(o.float()).all()
+        assert (o.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    qk, v = _rand_bf16((B * Q, 2 * C), 21, amp), _rand_bf16((B * Q, C), 22)
+    o = ops.attention(qk, qk, v, Q, Q, H, d_self, B, 1 / math.sqrt(d_self), 0, C, 0)
+    check(o, _attn_ref(r(qk[:, :C], Q, d_self), r(qk[:, C:], Q, d_self), r(v, Q, d_self), 1 / math.sqrt(d_self)), B * Q, C)
+    tq, kvq = _rand_bf16((B * Q, Ci), 23, amp), _rand_bf16((B * N, 3 * Ci), 24)
+    kvq[:, :Ci] *= amp
+    kvq[:, 2 * Ci:] *= amp
+    o = ops.attention(tq, kvq, kvq, Q, N, H, d_cross, B, 1 / math.sqrt(d_cross), 0, 0, Ci)
+    check(o, _attn_ref(r(tq, Q, d_cross), r(kvq[:, :Ci], N, d_cross), r(kvq[:, Ci:2 * Ci], N, d_cross), 1 / math.sqrt(d_cross)),
+          B * Q, Ci)
+    ik, iv = _rand_bf16((B * Q, Ci), 25, amp), _rand_bf16((B * Q, Ci), 26)
+    o = ops.attention(kvq, ik, iv, N, Q, H, d_cross, B, 1 / math.sqrt(d_cross), 2 * Ci, 0, 0, out_cols=Ci)
+    check(o, _attn_ref(r(kvq[:, 2 * Ci:], N, d_cross), r(ik, Q, d_cross), r(iv, Q, d_cross), 1 / math.sqrt(d_cross)), B * N, Ci)
 
 
 @pytest.mark.parametrize("C", [768, 1024, 1280])

@@ -3,7 +3,7 @@
 # drift by ~10 % between runs, so single runs do not compare).  usage: ROUNDS=3 tools/ab_bench.sh libA.so libB.so ...
 for i in $(seq ${ROUNDS:-3}); do
   for L in "$@"; do
-    VPU_LIB_PATH=$L python bench.py --no-e2e --no-cpu-baseline --profile-steps 0 --steps 40 2>/dev/null > /tmp/ab_line.json
+    VPU_LIB_PATH=$L python bench.py --no-e2e --no-cpu-baseline --no-noc --no-eager --profile-steps 0 --steps 40 2>/dev/null > /tmp/ab_line.json
     python - "$L" <<'PY'
 import json, sys
 d = json.loads(open('/tmp/ab_line.json').read().strip().splitlines()[-1])
