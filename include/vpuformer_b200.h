@@ -111,6 +111,10 @@ int vpu_coord_features(vpu_handle h, const float* image4, const vpu_prompts* pro
 int vpu_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* bias,
              const float* bias2d, int bias2d_rows, const void* residual, int residual_dtype, int ldr, int act /*0,1 gelu,2 relu*/,
              void* out, int out_dtype, int ldo, int impl /*0 tcgen05 (2-CTA pairs when the shape allows), 1 mma.sync cross-check, 2 tcgen05 1-CTA*/, void* stream);
+/* head pair of one pyramid level (reference swin_transformer.py:723-737), back to back with the [M,256] intermediate on chip:
+ * out[M,256] = bf16( bf16(relu(A[M,K1] * W1[256,K1]^T + bias1)) * W2[256,256]^T ) */
+int vpu_gemm_b2b(const void* A_bf16, int lda, const void* W1_bf16, const float* bias1, const void* W2_bf16, int M, int K1,
+                 void* out_bf16, int ldo, void* stream);
 /* ConvTranspose2d(k=2,s=2) as GEMM + pixel-shuffle store: A [B*g*g, K] -> out NHWC [B, 2g, 2g, cout] bf16 */
 int vpu_gemm_pixel_shuffle(const void* A_bf16, const void* W_bf16, int M, int cout, int K, const float* bias4, int g,
                            void* out_bf16, int impl, void* stream);

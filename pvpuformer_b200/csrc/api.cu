@@ -557,10 +557,21 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     for (int i = 0; i < 4; ++i) {
         const std::string si = std::to_string(i);
         const int rows = (int)(B * res[i] * res[i]);
-        RUN(f.gemm(f.buf<bf>(pyr[i]), od[i], "hd.c" + si + ".w", rows, hc, od[i], f.Wf("hd.c" + si + ".b"),
-                   f.buf<bf>(("HC" + si).c_str()), true, hc, ACT_RELU));
-        RUN(f.gemm(f.buf<bf>(("HC" + si).c_str()), hc, "hd.f" + si + ".w", rows, hc, hc, nullptr, f.buf<bf>(("Y" + si).c_str()),
-                   true, hc));
+        GemmB2B bb;
+        bb.A = f.buf<bf>(pyr[i]); bb.W1 = f.Wb("hd.c" + si + ".w"); bb.W2 = f.Wb("hd.f" + si + ".w"); bb.bias1 = f.Wf("hd.c" + si + ".b");
+        bb.out = f.buf<bf>(("Y" + si).c_str()); bb.M = rows; bb.K1 = od[i]; bb.lda = od[i]; bb.ldo = hc;
+        if (gemm_b2b_supported(bb, hc, hc)) {      // conv + ReLU + fusion-conv slice back to back, the intermediate stays on chip
+            f.label = "hd.c+f" + si + " " + std::to_string(rows) + "x" + std::to_string(hc) + "x" + std::to_string(od[i]);
+            const double by = 2.0 * ((double)rows * od[i] + (double)hc * od[i] + (double)hc * hc + (double)rows * hc);
+            const int brc = f.timed("gemm", 2.0 * rows * hc * ((double)od[i] + hc), by, [&] { return gemm_b2b_launch(bb, s); });
+            f.label.clear();
+            if (brc) return brc;
+        } else {
+            RUN(f.gemm(f.buf<bf>(pyr[i]), od[i], "hd.c" + si + ".w", rows, hc, od[i], f.Wf("hd.c" + si + ".b"),
+                       f.buf<bf>(("HC" + si).c_str()), true, hc, ACT_RELU));
+            RUN(f.gemm(f.buf<bf>(("HC" + si).c_str()), hc, "hd.f" + si + ".w", rows, hc, hc, nullptr, f.buf<bf>(("Y" + si).c_str()),
+                       true, hc));
+        }
         hca.y[i] = f.buf<bf>(("Y" + si).c_str());
         hca.res[i] = (int)res[i];
     }
@@ -853,6 +864,16 @@ int vpu_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K
     p.epi.bias2d_rows = bias2d_rows; p.epi.res = residual; p.epi.res_bf16 = residual_dtype == VPU_BF16; p.epi.ldr = ldr;
     p.epi.act = act;
     return gemm_launch(p, reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int vpu_gemm_b2b(const void* A, int lda, const void* W1, const float* bias1, const void* W2, int M, int K1, void* out, int ldo,
+                 void* stream) {
+    VPU_REQUIRE(A && W1 && W2 && bias1 && out, "vpu_gemm_b2b: null argument");
+    GemmB2B p;
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A); p.W1 = reinterpret_cast<const __nv_bfloat16*>(W1);
+    p.W2 = reinterpret_cast<const __nv_bfloat16*>(W2); p.bias1 = bias1; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.M = M; p.K1 = K1; p.lda = lda; p.ldo = ldo;
+    return gemm_b2b_launch(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vpu_gemm_pixel_shuffle(const void* A, const void* W, int M, int cout, int K, const float* bias4, int g, void* out, int impl,

@@ -967,6 +967,12 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t c
     return 0;
 }
 
+int gemm_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    if (int rc = gemm_init()) return rc;
+    return make_tmap(tm, ptr, rows, cols, ld, box_rows);
+}
+int gemm_num_sms() { return g_num_sms; }
+
 template <int BN, int EK = EK_GENERIC>
 static int launch_tc(const GemmProblem& p, cudaStream_t stream) {
     CUtensorMap tmA, tmB;

@@ -79,5 +79,24 @@ struct GemmProblem {
 // impl: 0 = tcgen05/TMA (product path), 1 = mma.sync reference kernel (debug / cross-check only)
 int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl = 0);
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes; idempotent
+// cached 2-D tensor map over a bf16 [rows, cols] matrix with leading dimension ld: box = 64 columns x box_rows rows, 128-byte swizzle
+int gemm_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int gemm_num_sms();
+
+// Back-to-back GEMM pair of the segmentation head (gemm_b2b.cu): per pyramid level the 1x1 conv + ReLU and that level's
+// [256, 256] slice of the fusion conv (reference swin_transformer.py:723-737; the slice is applied at native resolution
+// because a 1x1 conv commutes with the bilinear resize),
+//     Y[M, 256] = bf16( bf16(relu(A[M, K1] W1^T + b1)) W2^T ),
+// with the [M, 256] intermediate living only in shared memory (it was 2 x 411 MB of HBM traffic per batch-64 step at 1/4 res).
+struct GemmB2B {
+    const __nv_bfloat16* A = nullptr;   // [M, lda]
+    const __nv_bfloat16* W1 = nullptr;  // [256, K1]
+    const __nv_bfloat16* W2 = nullptr;  // [256, 256]
+    const float* bias1 = nullptr;       // [256]
+    __nv_bfloat16* out = nullptr;       // [M, ldo]
+    int M = 0, K1 = 0, lda = 0, ldo = 0;
+};
+bool gemm_b2b_supported(const GemmB2B& p, int n1, int n2);
+int gemm_b2b_launch(const GemmB2B& p, cudaStream_t stream);
 
 }  // namespace vpu

@@ -27,6 +27,15 @@ def gemm(A, W, bias=None, bias2d=None, residual=None, act=None, out_dtype=torch.
     return out
 
 
+def gemm_b2b(A, W1, bias1, W2):
+    """bf16( bf16(relu(A @ W1.T + bias1)) @ W2.T ): the head's conv + ReLU + fusion-conv slice of one pyramid level."""
+    M, K1 = A.shape
+    out = torch.empty(M, W2.shape[0], dtype=torch.bfloat16, device=A.device)
+    L.check(L.load().vpu_gemm_b2b(L.ptr(A), A.stride(0), L.ptr(W1), L.ptr(bias1), L.ptr(W2), M, K1, L.ptr(out), out.stride(0),
+                                  L.current_stream()))
+    return out
+
+
 def gemm_pixel_shuffle(A, W, bias4, g, cout, impl=0):
     """ConvTranspose2d(k=2,s=2): A [B*g*g, K] bf16, W [4*cout, K] -> NHWC [B, 2g, 2g, cout] bf16."""
     M, K = A.shape

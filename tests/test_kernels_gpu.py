@@ -79,6 +79,24 @@ def test_gemm_epilogues(impl):
     assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,K1", [(256, 128), (12544, 1024), (3136 * 3, 256), (50176, 512), (802816 // 8, 128)])
+def test_gemm_b2b_head_pair(M, K1):
+    """Back-to-back head GEMM (csrc/gemm_b2b.cu): conv 1x1 + ReLU + fusion-conv slice of one pyramid level with the
+    intermediate in shared memory, against the same two products in fp32 with the intermediate rounded to bf16 (what
+    the two separate GEMMs store).  M covers one tile, a ragged last tile (9408 = 36.75 x 256) and many tiles per CTA pair."""
+    from pvpuformer_b200 import ops
+    A = _rand_bf16((M, K1), 31)
+    W1, W2 = _rand_bf16((256, K1), 32, K1 ** -0.5), _rand_bf16((256, 256), 33, 1 / 16)
+    b1 = torch.randn(256, generator=torch.Generator().manual_seed(34)).to(_dev())
+    out = ops.gemm_b2b(A, W1, b1, W2)
+    h = torch.relu(A.float() @ W1.float().t() + b1).to(torch.bfloat16).float()
+    ref = h @ W2.float().t()
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    assert torch.equal(out, ops.gemm_b2b(A, W1, b1, W2))     # run to run
+
+
 @pytest.mark.parametrize("impl", [0, 2])
 def test_gemm_pixel_shuffle_matches_conv_transpose(impl):
     from pvpuformer_b200 import ops
