@@ -111,6 +111,13 @@ int vpu_coord_features(vpu_handle h, const float* image4, const vpu_prompts* pro
 int vpu_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* bias,
              const float* bias2d, int bias2d_rows, const void* residual, int residual_dtype, int ldr, int act /*0,1 gelu,2 relu*/,
              void* out, int out_dtype, int ldo, int impl /*0 tcgen05 (2-CTA pairs when the shape allows), 1 mma.sync cross-check, 2 tcgen05 1-CTA*/, void* stream);
+/* tail of the head at 1/4 resolution (reference swin_transformer.py:727-767): y_l = per-level fusion-conv slices, NHWC bf16
+ * [B, res0 >> l, res0 >> l, 256].  f = relu(bias + y_0 + sum_l resize_bilinear(y_l)) (never stored);
+ * seg_out[B, res0, res0] = <f, wseg> + seg_bias;  aux_out[B, nq, res0, res0] = (<f/|f|, qn[b, n]> + 1) / 2 (qn: unit rows,
+ * bf16 [B, 64, 256]; aux_out may be NULL) */
+int vpu_head_tail(const void* y0_bf16, const void* y1_bf16, const void* y2_bf16, const void* y3_bf16, int B, int res0,
+                  const float* bias, const float* wseg, float seg_bias, const void* qn_bf16, int nq, float* seg_out,
+                  float* aux_out, void* stream);
 /* head pair of one pyramid level (reference swin_transformer.py:723-737), back to back with the [M,256] intermediate on chip:
  * out[M,256] = bf16( bf16(relu(A[M,K1] * W1[256,K1]^T + bias1)) * W2[256,256]^T ) */
 int vpu_gemm_b2b(const void* A_bf16, int lda, const void* W1_bf16, const float* bias1, const void* W2_bf16, int M, int K1,

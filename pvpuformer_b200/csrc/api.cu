@@ -12,6 +12,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "head_tail.cuh"
 #include "noc.cuh"
 #include "prompt.cuh"
 #include "raster.cuh"
@@ -560,7 +561,8 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         GemmB2B bb;
         bb.A = f.buf<bf>(pyr[i]); bb.W1 = f.Wb("hd.c" + si + ".w"); bb.W2 = f.Wb("hd.f" + si + ".w"); bb.bias1 = f.Wf("hd.c" + si + ".b");
         bb.out = f.buf<bf>(("Y" + si).c_str()); bb.M = rows; bb.K1 = od[i]; bb.lda = od[i]; bb.ldo = hc;
-        if (gemm_b2b_supported(bb, hc, hc)) {      // conv + ReLU + fusion-conv slice back to back, the intermediate stays on chip
+        static const bool use_b2b = [] { const char* e = vpu_debug_env("VPU_HEAD_B2B"); return !(e && e[0] == '0'); }();   // A/B knob, -DVPU_DEBUG builds
+        if (use_b2b && gemm_b2b_supported(bb, hc, hc)) {      // conv + ReLU + fusion-conv slice back to back, the intermediate stays on chip
             f.label = "hd.c+f" + si + " " + std::to_string(rows) + "x" + std::to_string(hc) + "x" + std::to_string(od[i]);
             const double by = 2.0 * ((double)rows * od[i] + (double)hc * od[i] + (double)hc * hc + (double)rows * hc);
             const int brc = f.timed("gemm", 2.0 * rows * hc * ((double)od[i] + hc), by, [&] { return gemm_b2b_launch(bb, s); });
@@ -575,21 +577,36 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         hca.y[i] = f.buf<bf>(("Y" + si).c_str());
         hca.res[i] = (int)res[i];
     }
-    hca.bias = f.Wf("hd.f.b"); hca.out = f.buf<bf>("F"); hca.rnorm = f.buf<float>("rnorm"); hca.B = B;
-    hca.wseg = f.Wf("hd.seg.w"); hca.seg_bias = h.scalars.at("hd.seg.b"); hca.seg_out = f.buf<float>("seg_low");
-    RUN(f.timed("head_combine", 0, (double)B * hc * 2.0 * (2.0 * g4 * g4 + g2 * g2 + (double)g * g + gh * gh), [&] { return head_combine_launch(hca, s); }));
-    if (aux) {   // P2CL cosine logits (swin_transformer.py:745-756); skipped when the caller only reads 'instances'
+    HeadTailArgs ht;
+    for (int i = 0; i < 4; ++i) { ht.y[i] = hca.y[i]; ht.res[i] = hca.res[i]; }
+    ht.B = B; ht.channels = hc; ht.bias = f.Wf("hd.f.b"); ht.wseg = f.Wf("hd.seg.w"); ht.seg_bias = h.scalars.at("hd.seg.b");
+    ht.seg_out = f.buf<float>("seg_low"); ht.nq = Q;
+    if (aux) {   // P2CL queries (swin_transformer.py:745-750); skipped when the caller only reads 'instances'
         RUN(f.gemm(f.buf<bf>("qout_b"), C, "hd.q.w1", MQ, 2 * C, C, f.Wf("hd.q.b1"), f.buf<bf>("QF"), true, 2 * C, ACT_RELU));
         RUN(f.gemm(f.buf<bf>("QF"), 2 * C, "hd.q.w2", MQ, hc, 2 * C, f.Wf("hd.q.b2"), f.buf<float>("QE"), false, hc));
         RUN(f.timed("head_queries", 0, (double)B * 64 * hc * 6.0, [&] { return head_queries_launch(f.buf<float>("QE"), f.Wf("hd.seg.w"), B, Q, f.buf<bf>("QN"), s); }));
-        GemmProblem p;
-        p.A = f.buf<bf>("F"); p.W = f.buf<bf>("QN"); p.M = (int)(B * g4 * g4); p.N = 64; p.K = hc; p.lda = hc; p.ldw = hc;
-        p.w_rows = B * 64;
-        p.epi.mode = EPI_HEAD_FINAL; p.epi.m_per_batch = (int)(g4 * g4); p.epi.b_rows_per_batch = 64;
-        p.epi.rnorm = f.buf<float>("rnorm"); p.epi.aux_out = f.buf<float>("aux_low");
-        p.epi.seg_out = nullptr; p.epi.seg_bias = 0.f; p.epi.nq = Q;
-        const double by = (double)p.M * (hc * 2.0 + 4.0 + Q * 4.0);
-        RUN(f.timed("gemm", 2.0 * p.M * 64.0 * hc, by, [&] { return gemm_launch(p, s, h.gemm_impl); }));
+        ht.qn = f.buf<bf>("QN"); ht.aux_out = f.buf<float>("aux_low");
+    }
+    static const bool use_head_tail = [] { const char* e = vpu_debug_env("VPU_HEAD_TAIL"); return !(e && e[0] == '0'); }();   // A/B knob, -DVPU_DEBUG builds
+    if (use_head_tail && head_tail_supported(ht)) {
+        // resize + sum + ReLU + conv_seg + cosine logits on the tensor core: f never exists in memory (head_tail.cu)
+        const double px = (double)B * g4 * g4;
+        const double by = (double)B * hc * 2.0 * ((double)g4 * g4 + g2 * g2 + (double)g * g + gh * gh) + px * 4.0 + (aux ? px * Q * 4.0 : 0.0);
+        RUN(f.timed("head_tail", 2.0 * px * hc * (240.0 + (aux ? Q : 0)), by, [&] { return head_tail_launch(ht, s); }));
+    } else {
+        hca.bias = f.Wf("hd.f.b"); hca.out = f.buf<bf>("F"); hca.rnorm = f.buf<float>("rnorm"); hca.B = B;
+        hca.wseg = f.Wf("hd.seg.w"); hca.seg_bias = h.scalars.at("hd.seg.b"); hca.seg_out = f.buf<float>("seg_low");
+        RUN(f.timed("head_combine", 0, (double)B * hc * 2.0 * (2.0 * g4 * g4 + g2 * g2 + (double)g * g + gh * gh), [&] { return head_combine_launch(hca, s); }));
+        if (aux) {
+            GemmProblem p;
+            p.A = f.buf<bf>("F"); p.W = f.buf<bf>("QN"); p.M = (int)(B * g4 * g4); p.N = 64; p.K = hc; p.lda = hc; p.ldw = hc;
+            p.w_rows = B * 64;
+            p.epi.mode = EPI_HEAD_FINAL; p.epi.m_per_batch = (int)(g4 * g4); p.epi.b_rows_per_batch = 64;
+            p.epi.rnorm = f.buf<float>("rnorm"); p.epi.aux_out = f.buf<float>("aux_low");
+            p.epi.seg_out = nullptr; p.epi.seg_bias = 0.f; p.epi.nq = Q;
+            const double by = (double)p.M * (hc * 2.0 + 4.0 + Q * 4.0);
+            RUN(f.timed("gemm", 2.0 * p.M * 64.0 * hc, by, [&] { return gemm_launch(p, s, h.gemm_impl); }));
+        }
     }
     // ---- A17: final upsampling (align_corners=True) ----
     f.stage = "final";
@@ -792,6 +809,8 @@ int vpu_finalize(vpu_handle h) {
     }
     VPU_REQUIRE(h->scalars.count("hd.seg.b"), "scalar 'hd.seg.b' is not set");
     if (int rc = gemm_init()) return rc;
+    if (h->d.head_channels == 256 && (4 * h->grid()) % 16 == 0)       // interpolation-matrix table of the fused head tail
+        if (int rc = head_tail_prepare(4 * h->grid())) return rc;
     h->finalized = true;
     return 0;
 }
@@ -874,6 +893,19 @@ int vpu_gemm_b2b(const void* A, int lda, const void* W1, const float* bias1, con
     p.W2 = reinterpret_cast<const __nv_bfloat16*>(W2); p.bias1 = bias1; p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.M = M; p.K1 = K1; p.lda = lda; p.ldo = ldo;
     return gemm_b2b_launch(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vpu_head_tail(const void* y0, const void* y1, const void* y2, const void* y3, int B, int res0, const float* bias, const float* wseg,
+                  float seg_bias, const void* qn, int nq, float* seg_out, float* aux_out, void* stream) {
+    VPU_REQUIRE(y0 && y1 && y2 && y3 && bias && wseg && seg_out, "vpu_head_tail: null argument");
+    VPU_REQUIRE(!aux_out || qn, "vpu_head_tail: aux_out needs the normalised queries");
+    HeadTailArgs a;
+    a.y[0] = reinterpret_cast<const __nv_bfloat16*>(y0); a.y[1] = reinterpret_cast<const __nv_bfloat16*>(y1);
+    a.y[2] = reinterpret_cast<const __nv_bfloat16*>(y2); a.y[3] = reinterpret_cast<const __nv_bfloat16*>(y3);
+    for (int l = 0; l < 4; ++l) a.res[l] = res0 >> l;
+    a.B = B; a.channels = 256; a.bias = bias; a.wseg = wseg; a.seg_bias = seg_bias;
+    a.qn = reinterpret_cast<const __nv_bfloat16*>(qn); a.nq = nq; a.seg_out = seg_out; a.aux_out = aux_out;
+    return head_tail_launch(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vpu_gemm_pixel_shuffle(const void* A, const void* W, int M, int cout, int K, const float* bias4, int g, void* out, int impl,

@@ -58,6 +58,8 @@ SIGNATURES = {
     "vpu_coord_features": (c_int, [c_void_p, c_void_p, POINTER(VpuPrompts), c_int, c_void_p, c_void_p]),
     "vpu_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                          c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vpu_head_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                              c_void_p, c_void_p]),
     "vpu_gemm_b2b": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "vpu_gemm_pixel_shuffle": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "vpu_attention": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,

@@ -36,6 +36,16 @@ def gemm_b2b(A, W1, bias1, W2):
     return out
 
 
+def head_tail(ys, bias, wseg, seg_bias, qn=None, nq=48):
+    """ys: four NHWC bf16 maps [B, R >> l, R >> l, 256]; -> (seg [B, R, R] fp32, aux [B, nq, R, R] fp32 or None)."""
+    B, R = ys[0].shape[0], ys[0].shape[1]
+    seg = torch.empty(B, R, R, dtype=torch.float32, device=ys[0].device)
+    aux = torch.empty(B, nq, R, R, dtype=torch.float32, device=ys[0].device) if qn is not None else None
+    L.check(L.load().vpu_head_tail(L.ptr(ys[0]), L.ptr(ys[1]), L.ptr(ys[2]), L.ptr(ys[3]), B, R, L.ptr(bias), L.ptr(wseg),
+                                   float(seg_bias), L.ptr(qn), nq, L.ptr(seg), L.ptr(aux), L.current_stream()))
+    return seg, aux
+
+
 def gemm_pixel_shuffle(A, W, bias4, g, cout, impl=0):
     """ConvTranspose2d(k=2,s=2): A [B*g*g, K] bf16, W [4*cout, K] -> NHWC [B, 2g, 2g, cout] bf16."""
     M, K = A.shape

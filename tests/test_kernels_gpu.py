@@ -97,6 +97,39 @@ def test_gemm_b2b_head_pair(M, K1):
     assert torch.equal(out, ops.gemm_b2b(A, W1, b1, W2))     # run to run
 
 
+@pytest.mark.parametrize("B,R,aux", [(1, 112, True), (3, 112, True), (5, 112, False), (2, 128, True), (151, 112, True)])
+def test_head_tail_resize_sum_seg_and_cosine_logits(B, R, aux):
+    """Fused head tail (csrc/head_tail.cu): relu(b + y0 + sum_l resize(y_l)) -> conv_seg and P2CL cosine logits, with the
+    bilinear resize (align_corners=False, swin_transformer.py:727-737) done as a tensor-core product with precomputed tap
+    matrices, against F.interpolate in fp32.  B = 3 / 151 put image boundaries inside a CTA's tile range (query reload),
+    R = 128 is the ViT-H geometry, more tiles than 2 x SMs exercise the accumulator double buffering."""
+    from pvpuformer_b200 import ops
+    ys = [_rand_bf16((B, R >> l, R >> l, 256), 40 + l) for l in range(4)]
+    g = torch.Generator().manual_seed(45)
+    bias, wseg = torch.randn(256, generator=g).to(_dev()), (torch.randn(256, generator=g) / 16).to(_dev())
+    qn = torch.zeros(B, 64, 256)
+    qn[:, :48] = F.normalize(torch.randn(B, 48, 256, generator=g), dim=2)
+    qn = qn.to(torch.bfloat16).to(_dev())
+    seg, auxo = ops.head_tail(ys, bias, wseg, 0.25, qn if aux else None)
+    f = bias.view(1, 256, 1, 1) + ys[0].float().permute(0, 3, 1, 2)
+    for l in range(1, 4):
+        f = f + F.interpolate(ys[l].float().permute(0, 3, 1, 2), size=(R, R), mode="bilinear", align_corners=False)
+    f = torch.relu(f)
+    seg_ref = (f * wseg.view(1, 256, 1, 1)).sum(1) + 0.25
+    assert torch.isfinite(seg).all()
+    assert (seg - seg_ref).abs().max().item() < 1e-3 * max(1.0, seg_ref.abs().max().item())
+    if aux:
+        fn = F.normalize(f, dim=1).to(torch.bfloat16).float()      # the kernel rounds f to bf16 for the product, like the stored F did
+        ref = (torch.einsum("bnc,bchw->bnhw", qn[:, :48].float(), F.normalize(f, dim=1)) + 1) / 2
+        assert torch.isfinite(auxo).all()
+        assert (auxo - ref).abs().max().item() < 4e-3
+        del fn
+    else:
+        assert auxo is None
+    seg2, aux2 = ops.head_tail(ys, bias, wseg, 0.25, qn if aux else None)
+    assert torch.equal(seg, seg2) and (not aux or torch.equal(auxo, aux2))
+
+
 @pytest.mark.parametrize("impl", [0, 2])
 def test_gemm_pixel_shuffle_matches_conv_transpose(impl):
     from pvpuformer_b200 import ops
