@@ -14,6 +14,14 @@
 //                   18 output stores (four TMA tensor stores per tile: an epilogue thread owns a row, so direct global stores touch
 //                   32 lines per instruction; measured 222 us with them against 155 us without any store at 1/4 resolution)
 // Per tile: MMA1(i) -> epi1(i) chunk by chunk || MMA2(i) k-chunk by k-chunk -> MMA1(i+1) -> epi2(i) || epi1(i+1) ...
+//
+// Two negative results of round 2, kept out of the code:
+//   * H through shared memory (generic-proxy stores of both CTAs -> fence.proxy.async -> mbarrier with .release.cluster /
+//     .acquire.cluster): the cluster-scope semantics compile to MEMBAR + ERRBAR + an L1 invalidate (CCTL.IVALL) per wait
+//     iteration; 258 us at 1/4 resolution against 130 us with H in TMEM.
+//   * the producing branch's GroupNorm + GELU applied to the A k-chunks in shared memory by extra warps (instead of the separate
+//     gn_apply pass): the kernel becomes issue-bound (7 FMA + 2 MUFU per element on top of both epilogues) and gains exactly what
+//     the removed passes cost (407 us against 229 + 181 us).
 #include "gemm.cuh"
 #include "tc_attn.cuh"
 
