@@ -218,9 +218,84 @@ __global__ void __launch_bounds__(256) patch_operand_kernel(const CoordArgs a, _
     }
 }
 
+
+// The same for 16-pixel patches (ViT-B / L): a WARP owns a patch, lane = (patch row, 8-pixel half), so that every store
+// instruction of the warp writes the 512 contiguous bytes one plane of one patch occupies in its A row (k = plane * 256 +
+// row * 16 + column) as 16-byte pieces.  The kernel above moves 4 bytes per store instruction to 4 different lines and ran at
+// 2.3 TB/s (store-instruction-bound: 2 M warp stores for 257 MB); this one issues a quarter of them.
+// grid (H / 16, B), block 256: the CTA owns one row of patches, warp w the patches w, w + 8, ...
+__global__ void __launch_bounds__(256) patch_operand16_kernel(const CoordArgs a, __nv_bfloat16* __restrict__ A, int lda) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int P = 16, PP = P * P;
+    __shared__ SmemPoints sp[P];
+    const int gy = blockIdx.x, b = blockIdx.y, H = a.H, W = a.W, g = W / P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float r2 = a.radius * a.radius;
+    if (threadIdx.x < 2 * P) {       // the clicks that can reach each of the 16 image rows, per half (positive / negative)
+        const int ry = threadIdx.x >> 1, h = threadIdx.x & 1, yy = gy * P + ry;
+        const double* pts = a.points + (size_t)b * 2 * a.n * 3;
+        int k = 0;
+        for (int i = 0; i < a.n; ++i) {
+            const double* p = pts + (size_t)(h * a.n + i) * 3;
+            if (fmax(p[0], p[1]) >= 0.0) {
+                const float dr = (float)((double)yy - p[0]);
+                const float d2 = __fmul_rn(dr, dr);
+                if (d2 <= r2) { sp[ry].pc[h * 24 + k] = p[1]; sp[ry].dr2[h * 24 + k] = d2; ++k; }
+            }
+        }
+        sp[ry].cnt[h] = k;
+    }
+    __syncthreads();
+    const int ph = lane >> 1, half = lane & 1, y = gy * P + ph;
+    for (int gx = warp; gx < g; gx += 8) {
+        const int x0 = gx * P + half * 8;
+        __nv_bfloat16* dst = A + ((size_t)b * g * (H / P) + (size_t)gy * g + gx) * lda + ph * P + half * 8;
+        float4 v[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4* src = reinterpret_cast<const float4*>(a.image4 + (((size_t)b * 4 + c) * H + y) * W + x0);
+            v[c][0] = src[0];
+            v[c][1] = src[1];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {      // split-bf16: v = hi + lo with |lo| <= 2^-9 |v|
+            const float f[8] = {v[c][0].x, v[c][0].y, v[c][0].z, v[c][0].w, v[c][1].x, v[c][1].y, v[c][1].z, v[c][1].w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                hi[q] = pack_bf16(f[2 * q], f[2 * q + 1]);
+                const float2 hf = unpack_bf16(hi[q]);
+                lo[q] = pack_bf16(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
+            }
+            *reinterpret_cast<uint4*>(dst + c * PP) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dst + (6 + c) * PP) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t w[4];
+            const uint8_t* em = a.extra_mask ? a.extra_mask + (((size_t)b * 2 + h) * H + y) * W + x0 : nullptr;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                bool h0 = disk_hit(sp[ph], h, x0 + 2 * q, r2), h1 = disk_hit(sp[ph], h, x0 + 2 * q + 1, r2);
+                if (em) { h0 |= em[2 * q] != 0; h1 |= em[2 * q + 1] != 0; }
+                w[q] = pack_bf16(h0 ? 1.f : 0.f, h1 ? 1.f : 0.f);
+            }
+            *reinterpret_cast<uint4*>(dst + (4 + h) * PP) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 int patch_operand_launch(const CoordArgs& a, int B, __nv_bfloat16* A, int patch, int lda, cudaStream_t stream) {
     VPU_REQUIRE(a.n >= 1 && a.n <= 24, "patch operand: n=%d outside [1, 24]", a.n);
     VPU_REQUIRE(patch % 2 == 0 && a.W % patch == 0 && a.H % patch == 0 && a.W % 2 == 0, "patch operand: bad geometry");
+    if (patch == 16 && lda % 8 == 0 && a.W % 16 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(a.image4) & 15) == 0) {
+        VPU_CHECK_CUDA(launch_pdl(patch_operand16_kernel, dim3(a.H / 16, B), dim3(256), 0, stream, a, A, lda));
+        VPU_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    }
     dim3 grid(a.H, B);
     int threads = a.W / 2;
     threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;
