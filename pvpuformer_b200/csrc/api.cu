@@ -117,7 +117,7 @@ Plan make_plan(const vpu_context& h, int B) {
     p.add("A0", M * h.K0s() * 2);
     p.add("X", M * C * 4);
     p.add("Xn", M * C * 2);
-    p.add("lnstats", M * (size_t)gemm_ln_slots((int)C) * sizeof(float2));
+    p.add("lnstats", M * (size_t)gemm_ln_slots_max((int)C) * sizeof(float2));
     p.add("lnrow", M * sizeof(float2));
     p.add("lncnt", (M / 32 + 2) * sizeof(int));       // arrival counters of the in-GEMM LayerNorm finalisation (zero between GEMMs)
     p.add("QKV", M * 3 * C * 2);
@@ -260,7 +260,7 @@ struct Fwd {
         if (gn) set_gn(p.epi, *gn);
         if (ln) {
             p.epi.ln_out = ln->out; p.epi.ln_out_bf16 = ln->out_bf16; p.epi.ln_in = ln->in; p.epi.ln_s = ln->s;
-            p.epi.ln_slots = gemm_ln_slots(h.C());
+            p.epi.ln_slots = gemm_ln_slots(M, h.C());
             if (ln->out && ln_in_gemm()) { p.epi.ln_row = ln->row; p.epi.ln_cnt = buf<int>("lncnt"); p.epi.ln_eps = ln->eps; }
         }
         const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0)) +

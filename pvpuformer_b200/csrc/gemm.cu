@@ -848,7 +848,13 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(const __nv_bfloat16* __re
 }
 #endif  // VPU_DEBUG
 
-int gemm_ln_slots(int N) { return ((N + 255) / 256) * EpiWarps<EK_F32_RES_LNOUT>::N; }
+// tile width of the LayerNorm-fused GEMMs: always 256.  128-wide tiles would put twice as many CTA pairs to work on a batch-2
+// forward (proj / fc2: 21 pair tiles for 74 pairs), but the statistics slots are per (column tile, epilogue warp): a tile width that
+// depends on M would change the fp32 grouping of the row sums with the batch size, and the forward is bit-identical for a sample
+// alone, first or in the middle of a batch (the lock-step NoC loop reproduces the serial one bit for bit because of that).
+static int ln_tile_bn(int, int) { return 256; }
+int gemm_ln_slots(int M, int N) { const int bn = ln_tile_bn(M, N); return ((N + bn - 1) / bn) * EpiWarps<EK_F32_RES_LNOUT>::N; }
+int gemm_ln_slots_max(int N) { return ((N + 127) / 128) * EpiWarps<EK_F32_RES_LNOUT>::N; }
 
 // Row statistics of the LayerNorm fusion: the slots a residual GEMM wrote (Epi::ln_out) -> (rstd, mean * rstd) per row, added in
 // slot order in double precision (one thread per row; 2.4 MB in, 0.4 MB out for ViT-B at batch 64).
@@ -885,6 +891,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
+static bool g_small_tiles = true;      // VPU_GEMM_SMALL_TILES=0 (-DVPU_DEBUG builds): the round-1 tile choice for small problems
 static bool g_use_2cta = true;
 static int g_stages = 0;
 static int g_cluster = 2;
@@ -965,6 +972,7 @@ int gemm_init() {
     if (const char* cl = vpu_debug_env("VPU_GEMM_CLUSTER")) g_cluster = atoi(cl) == 4 ? 4 : 2;
     if (const char* ab = vpu_debug_env("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
     if (const char* rg = vpu_debug_env("VPU_GEMM_RAGGED256")) g_ragged256 = rg[0] != '0';
+    if (const char* sm = vpu_debug_env("VPU_GEMM_SMALL_TILES")) g_small_tiles = sm[0] != '0';
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
@@ -1112,12 +1120,12 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
                     "LayerNorm-fused GEMM needs the 2-CTA kernel, N %% 256 == 0 and a plain epilogue (M=%d N=%d)", p.M, p.N);
         VPU_REQUIRE(e.ln_slots > 0 && e.bias, "LayerNorm-fused GEMM: ln_slots / bias missing");
         if (e.ln_out)
-            VPU_REQUIRE(!e.ln_in && !e.out_bf16 && e.res && !e.res_bf16 && e.act == ACT_NONE && e.ln_out_bf16 && e.ln_slots == gemm_ln_slots(p.N),
-                        "ln_out needs a fp32 output with fp32 residual, a bf16 copy buffer and ln_slots == %d", gemm_ln_slots(p.N));
+            VPU_REQUIRE(!e.ln_in && !e.out_bf16 && e.res && !e.res_bf16 && e.act == ACT_NONE && e.ln_out_bf16 && e.ln_slots == gemm_ln_slots(p.M, p.N),
+                        "ln_out needs a fp32 output with fp32 residual, a bf16 copy buffer and ln_slots == %d", gemm_ln_slots(p.M, p.N));
         else
             VPU_REQUIRE(e.out_bf16 && !e.res && e.ln_s && (e.act == ACT_NONE || e.act == ACT_GELU),
                         "ln_in needs a bf16 output without residual and ln_s");
-        return launch_tc2<256>(p, stream);
+        return ln_tile_bn(p.M, p.N) == 128 ? launch_tc2<128>(p, stream) : launch_tc2<256>(p, stream);
     }
     if (impl == 1) {
 #ifndef VPU_DEBUG
@@ -1134,6 +1142,9 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
     }
     // impl 0: 2-CTA pairs whenever the shape allows it; impl 2 forces the 1-CTA kernel (A/B comparison, tests)
     if (impl == 0 && g_use_2cta && p.epi.mode != EPI_HEAD_FINAL && p.M >= 2 * BM) {
+        // few tiles (the token-side projections of the DMA stage: M = 48 B rows): 128-wide tiles put twice as many CTA pairs to work
+        const long long tiles256 = (long long)((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + 255) / 256);
+        if (g_small_tiles && p.N % 256 == 0 && tiles256 * 4 <= g_num_sms) return launch_tc2<128>(p, stream);
         if (p.N % 256 == 0) return launch_tc2<256>(p, stream);
         // N = 128 (2k+1), k >= 2 (the DMA image-side K|V|Q projection, N = 1152): 256-wide tiles with a half-empty last tile
         // (TMA zero-fills the missing weight rows, the epilogue skips the missing columns) waste <= 1/5 of the MMA work but keep
@@ -1142,6 +1153,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         if (p.N % 128 == 0) return launch_tc2<128>(p, stream);
     }
     if (p.epi.mode == EPI_HEAD_FINAL) return launch_tc<64, EK_HEAD>(p, stream);
+    // one row tile (a handful of click sessions): the launch is bound by how fast its few CTAs pull the weights, so use many narrow tiles
+    if (g_small_tiles && p.M <= BM && p.N % 64 == 0 && p.N >= 128 && p.epi.mode == EPI_PLAIN) return launch_tc<64>(p, stream);
     if (p.N % 256 == 0) return launch_tc<256>(p, stream);
     if (p.N % 192 == 0) return launch_tc<192>(p, stream);
     if (p.N % 128 == 0) return launch_tc<128>(p, stream);

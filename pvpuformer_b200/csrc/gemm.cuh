@@ -68,8 +68,9 @@ struct Epi {
     float ln_eps = 1e-6f;
 };
 
-// slots per row of Epi::ln_out for an N-column residual GEMM (256-wide tiles x epilogue warps per TMEM lane quarter)
-int gemm_ln_slots(int N);
+// slots per row of Epi::ln_out for an [M, N] residual GEMM (column tiles x epilogue warps per TMEM lane quarter)
+int gemm_ln_slots(int M, int N);     // for the tile width the launch will choose for this shape (256, or 128 when that leaves SMs idle)
+int gemm_ln_slots_max(int N);        // buffer sizing
 // slots [M][P] -> (rstd, mean * rstd) [M] of a LayerNorm over C values with the given eps
 int ln_rowstats_launch(const float2* slots, int M, int P, int C, float eps, float2* out, cudaStream_t stream);
 
