@@ -408,18 +408,28 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                 }
             }
             __syncwarp();
+            if constexpr (LNOUT) {
+                // One slot per (128-column group of the row, epilogue warp), whatever the tile width: a warp's chunks are
+                // ew * 32 + 64 k, so its partial over a 128-column group is the same two chunks on 256- and 128-wide tiles and
+                // the statistics do not depend on the tile choice (which depends on M: see ln_tile_bn).  The 8 lanes that share
+                // a row (lane & 7) fold their partials in a fixed butterfly.
+                const int cn = c + EW * 32;
+                if (cn >= BN || col_base + cn >= d.N || (cn >> 7) != (c >> 7)) {
+                    const int slot = ((col_base + c) >> 7) * EW + ew;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        float sm = ln_sum[it], sq = ln_sq[it];
+#pragma unroll
+                        for (int o = 4; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+                        const int m = r_lo + 4 * it + sub;
+                        if ((lane & 7) == 0 && m < d.M) e.ln_out[(size_t)m * e.ln_slots + slot] = make_float2(sm, sq);
+                        ln_sum[it] = 0.f;
+                        ln_sq[it] = 0.f;
+                    }
+                }
+            }
         }
         if constexpr (LNOUT) {
-            // the 8 lanes that share a row (lane & 7) fold their partials in a fixed butterfly; one slot per (column tile, warp)
-            const int slot = (col_base / BN) * EW + ew;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                float sm = ln_sum[it], sq = ln_sq[it];
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
-                const int m = r_lo + 4 * it + sub;
-                if ((lane & 7) == 0 && m < d.M) e.ln_out[(size_t)m * e.ln_slots + slot] = make_float2(sm, sq);
-            }
             if (e.ln_row && r_lo < d.M) {     // (warp-uniform) blocks past the last row have no counter
                 // Finalisation by the last arrival: every (column tile, epilogue warp) of these 32 rows bumps the block's counter
                 // after its slot stores; whoever sees ln_slots - 1 adds the slots in INDEX order (the result does not depend on
@@ -429,7 +439,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                 __threadfence();
                 __syncwarp();
                 int last = 0;
-                if (lane == 0) last = atomicAdd(e.ln_cnt + (r_lo >> 5), 1) == e.ln_slots - 1;
+                if (lane == 0) last = atomicAdd(e.ln_cnt + (r_lo >> 5), 1) == ((d.N + BN - 1) / BN) * EW - 1;
                 last = __shfl_sync(0xffffffffu, last, 0);
                 if (last) {
                     __threadfence();
@@ -848,12 +858,16 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(const __nv_bfloat16* __re
 }
 #endif  // VPU_DEBUG
 
-// tile width of the LayerNorm-fused GEMMs: always 256.  128-wide tiles would put twice as many CTA pairs to work on a batch-2
-// forward (proj / fc2: 21 pair tiles for 74 pairs), but the statistics slots are per (column tile, epilogue warp): a tile width that
-// depends on M would change the fp32 grouping of the row sums with the batch size, and the forward is bit-identical for a sample
-// alone, first or in the middle of a batch (the lock-step NoC loop reproduces the serial one bit for bit because of that).
-static int ln_tile_bn(int, int) { return 256; }
-int gemm_ln_slots(int M, int N) { const int bn = ln_tile_bn(M, N); return ((N + bn - 1) / bn) * EpiWarps<EK_F32_RES_LNOUT>::N; }
+// Tile width of the LayerNorm-fused GEMMs: 256, or 128 when 256-wide tiles would occupy at most a quarter of the SMs (a batch-2
+// forward: proj / fc2 with 21 pair tiles for 74 CTA pairs).  The statistics slots are per 128-column group (epilogue_tile), so the
+// fp32 grouping of the row sums -- and with it every bit of the forward -- does not depend on this choice: a sample alone, first or in
+// the middle of a batch gives the same bits (the lock-step NoC loop reproduces the serial one bit for bit because of that).
+static int g_num_sms_for_tiles();
+static int ln_tile_bn(int M, int N) {
+    const long long tiles256 = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+    return (tiles256 * 4 <= g_num_sms_for_tiles() && N % 128 == 0) ? 128 : 256;
+}
+int gemm_ln_slots(int, int N) { return ((N + 127) / 128) * EpiWarps<EK_F32_RES_LNOUT>::N; }
 int gemm_ln_slots_max(int N) { return ((N + 127) / 128) * EpiWarps<EK_F32_RES_LNOUT>::N; }
 
 // Row statistics of the LayerNorm fusion: the slots a residual GEMM wrote (Epi::ln_out) -> (rstd, mean * rstd) per row, added in
@@ -898,6 +912,8 @@ static int g_cluster = 2;
 static int g_ablate = 0;
 static bool g_ragged256 = true;
 static std::mutex g_mu;
+
+static int g_num_sms_for_tiles() { return g_small_tiles ? (g_num_sms > 0 ? g_num_sms : 148) : 0; }
 
 struct TmKey {
     const void* p;
