@@ -119,7 +119,6 @@ Plan make_plan(const vpu_context& h, int B) {
     p.add("Xn", M * C * 2);
     p.add("lnstats", M * (size_t)gemm_ln_slots_max((int)C) * sizeof(float2));
     p.add("lnrow", M * sizeof(float2));
-    p.add("lncnt", (M / 32 + 2) * sizeof(int));       // arrival counters of the in-GEMM LayerNorm finalisation (zero between GEMMs)
     p.add("QKV", M * 3 * C * 2);
     p.add("AO", M * C * 2);
     p.add("H", M * 4 * C * 2);
@@ -239,14 +238,9 @@ struct Fwd {
         float eps = 1e-6f;
     };
     // The row statistics of the LayerNorm fusion are finalised by ln_rowstats_kernel, a launch of its own after every residual GEMM.
-    // Finalising them inside the producing GEMM (Epi::ln_row: the last-arriving column tile of a 32-row block adds the slots;
-    // VPU_LN_IN_GEMM=1 in -DVPU_DEBUG builds) removes 25 launches of 8 us and measured +0.3 ms per step in three A/B
-    // alternations (14.19 / 14.25 / 14.47 ms without, 14.56 / 14.55 / 14.75 ms with): the __threadfence before the arrival
-    // counter makes every epilogue warp of proj / fc2 wait for its own 40 KB of tile stores, which the kernel otherwise never does.
-    static bool ln_in_gemm() {
-        static const bool on = [] { const char* e = vpu_debug_env("VPU_LN_IN_GEMM"); return e && e[0] == '1'; }();
-        return on;
-    }
+    // Finalising them inside the producing GEMM (the last-arriving column tile of a 32-row block adds the slots, arrival counter
+    // + __threadfence) was tried in round 2: +0.3 ms per batch-64 step in three A/B alternations (the fence makes every epilogue
+    // warp of proj / fc2 wait for its own 40 KB of tile stores) and no gain at batch 2; removed.
     // out = act(A W^T + bias [+ tab] [+ res])
     int gemm(const __nv_bfloat16* A, int lda, const std::string& wkey, int M, int Nn, int K, const float* bias, void* out,
              bool out_bf16, int ldo, int act = ACT_NONE, const void* res = nullptr, bool res_bf16 = false, int ldr = 0,
@@ -261,7 +255,6 @@ struct Fwd {
         if (ln) {
             p.epi.ln_out = ln->out; p.epi.ln_out_bf16 = ln->out_bf16; p.epi.ln_in = ln->in; p.epi.ln_s = ln->s;
             p.epi.ln_slots = gemm_ln_slots(M, h.C());
-            if (ln->out && ln_in_gemm()) { p.epi.ln_row = ln->row; p.epi.ln_cnt = buf<int>("lncnt"); p.epi.ln_eps = ln->eps; }
         }
         const double by = 2.0 * ((double)M * K + (double)Nn * K) + (double)M * Nn * ((out_bf16 ? 2 : 4) + (res ? (res_bf16 ? 2 : 4) : 0)) +
                           (ln && ln->out ? 2.0 * M * Nn : 0.0);
@@ -269,7 +262,7 @@ struct Fwd {
         const int grc = timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
         label.clear();
         if (grc) return grc;
-        if (ln && ln->out && !ln_in_gemm())      // separate finalisation of the row statistics (A/B knob only)
+        if (ln && ln->out)      // finalise the row statistics for the LayerNorm-folded GEMM that follows
             return timed("lnstats", 0, (double)M * (p.epi.ln_slots + 1) * 8.0,
                          [&] { return ln_rowstats_launch(ln->out, M, p.epi.ln_slots, h.C(), ln->eps, ln->row, s); });
         return 0;
@@ -357,7 +350,6 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     // GroupNorm accumulators of the neck: cleared here so that no memset node sits between two kernels later on
     // (a non-kernel node would break the programmatic-dependent-launch chain, common.cuh)
     VPU_CHECK_CUDA(cudaMemsetAsync(f.buf<long long>("gn_sums"), 0, (size_t)8 * B * 2 * sizeof(long long), s));
-    VPU_CHECK_CUDA(cudaMemsetAsync(f.buf<int>("lncnt"), 0, ((size_t)B * h.N() / 32 + 2) * sizeof(int), s));
     // ---- A1-A3, A7: fused image + coord-feature patch operand, one GEMM for both patch embeds ----
     CoordArgs ca;
     ca.image4 = image4; ca.points = pr.points; ca.extra_mask = pr.extra_mask; ca.n = pr.n; ca.H = img; ca.W = img;

@@ -429,36 +429,6 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, const GemmDims& d, u
                 }
             }
         }
-        if constexpr (LNOUT) {
-            if (e.ln_row && r_lo < d.M) {     // (warp-uniform) blocks past the last row have no counter
-                // Finalisation by the last arrival: every (column tile, epilogue warp) of these 32 rows bumps the block's counter
-                // after its slot stores; whoever sees ln_slots - 1 adds the slots in INDEX order (the result does not depend on
-                // which warp that is) in double precision, like ln_rowstats_kernel did in a launch of its own (8 us x 25 per
-                // ViT-B forward, 9 us x 65 per ViT-H forward).  Slots are re-read past L1 (ld.global.cg): the same addresses were
-                // read by the previous GEMM's finalisation and may be stale there.
-                __threadfence();
-                __syncwarp();
-                int last = 0;
-                if (lane == 0) last = atomicAdd(e.ln_cnt + (r_lo >> 5), 1) == ((d.N + BN - 1) / BN) * EW - 1;
-                last = __shfl_sync(0xffffffffu, last, 0);
-                if (last) {
-                    __threadfence();
-                    const int m = r_lo + lane;
-                    if (m < d.M) {
-                        double S = 0.0, Q = 0.0;
-                        for (int k = 0; k < e.ln_slots; ++k) {
-                            const float2 t = __ldcg(e.ln_out + (size_t)m * e.ln_slots + k);
-                            S += (double)t.x; Q += (double)t.y;
-                        }
-                        const double inv_c = 1.0 / (double)d.N, mean = S * inv_c;
-                        const double var = fmax(Q * inv_c - mean * mean, 0.0);
-                        const float rstd = (float)(1.0 / sqrt(var + (double)e.ln_eps));
-                        e.ln_row[m] = make_float2(rstd, (float)mean * rstd);
-                    }
-                    if (lane == 0) e.ln_cnt[r_lo >> 5] = 0;
-                }
-            }
-        }
         if (stats) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -60,12 +60,6 @@ struct Epi {
     const float2* ln_in = nullptr;
     const float* ln_s = nullptr;
     int ln_slots = 0;
-    //   ln_row      with ln_out: the warp that writes the LAST slot of a 32-row block (ln_cnt[block], a self-resetting arrival
-    //               counter that must be zero on entry) adds the block's slots in index order and writes (rstd, mean * rstd) [M]
-    //               here -- the ln_in of the consuming GEMM -- so no separate finalisation kernel runs between the two GEMMs
-    float2* ln_row = nullptr;
-    int* ln_cnt = nullptr;
-    float ln_eps = 1e-6f;
 };
 
 // slots per row of Epi::ln_out for an [M, N] residual GEMM (column tiles x epilogue warps per TMEM lane quarter)
