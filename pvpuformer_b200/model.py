@@ -285,23 +285,31 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
     def _forward_graph(self, image, pts, B, want_aux, device):
         """Small click-prompt batches: vpu_forward never allocates or synchronises and enqueues on one stream only, so the
         whole forward is captured once into a CUDA graph over static input / output buffers and replayed per call (copy the
-        inputs in, replay, clone the outputs out).  The graph holds the workspace address: it is re-captured if a larger
-        batch has replaced the workspace since."""
-        s, n2 = self.cfg.img_size, pts.shape[1]
+        inputs in, replay, clone the outputs out).  The click rows are re-laid out into the full 2 x num_max_points slots
+        (unused slots = (-1, -1, -1), exactly what the reference pads with, is_vpu_model.py:218-228), so one graph per
+        (batch, aux) serves a session whose click count grows with every click.  The graph holds the workspace address: it is
+        re-captured if a larger batch has replaced the workspace since."""
+        s, n, nm = self.cfg.img_size, pts.shape[1] // 2, self.num_max_points
         ws = self.workspace(B, device)
-        key = (B, n2, want_aux, device)
+        key = (B, want_aux, device)
         g = self._graphs.get(key)
         stream = self._serialize_streams()
+
+        def load_inputs():
+            g["image"].copy_(image)
+            g["pts"].fill_(-1.0)
+            g["pts"][:, :n].copy_(pts[:, :n])
+            g["pts"][:, nm:nm + n].copy_(pts[:, n:])
         if g is None or g["ws_ptr"] != ws.data_ptr():
-            g = {"ws_ptr": ws.data_ptr(), "image": torch.empty_like(image), "pts": torch.empty_like(pts),
+            g = {"ws_ptr": ws.data_ptr(), "image": torch.empty_like(image),
+                 "pts": torch.empty(B, 2 * nm, 3, dtype=torch.float64, device=device),
                  "inst": torch.empty(B, 1, s, s, dtype=torch.float32, device=device),
                  "aux": torch.empty(B, self.cfg.num_queries, s, s, dtype=torch.float32, device=device) if want_aux else None}
             pr = L.VpuPrompts()
             pr.points = g["pts"].data_ptr()
-            pr.n = n2 // 2
+            pr.n = nm
             pr.type = 0
-            g["image"].copy_(image)
-            g["pts"].copy_(pts)
+            load_inputs()
 
             def enqueue():
                 L.check(L.load().vpu_forward(self._handle, L.ptr(g["image"]), ctypes.byref(pr), B, L.ptr(g["inst"]), L.ptr(g["aux"]),
@@ -313,8 +321,7 @@ class VitMultiGaussianVector_ed_Model(nn.Module):
                 enqueue()
             g["graph"] = graph
             self._graphs[key] = g
-        g["image"].copy_(image)
-        g["pts"].copy_(pts)
+        load_inputs()
         g["graph"].replay()
         self._mark_use(stream)
         return {"instances": g["inst"].clone(), "instances_aux": g["aux"].clone() if want_aux else None}
