@@ -881,6 +881,7 @@ static int g_stages = 0;
 static int g_cluster = 2;
 static int g_ablate = 0;
 static bool g_ragged256 = true;
+static int g_res_kmax = 1 << 30;       // VPU_GEMM_RES_KMAX (-DVPU_DEBUG builds): largest K that takes gemm_res.cu (0 = never)
 static std::mutex g_mu;
 
 static int g_num_sms_for_tiles() { return g_small_tiles ? (g_num_sms > 0 ? g_num_sms : 148) : 0; }
@@ -958,6 +959,7 @@ int gemm_init() {
     if (const char* cl = vpu_debug_env("VPU_GEMM_CLUSTER")) g_cluster = atoi(cl) == 4 ? 4 : 2;
     if (const char* ab = vpu_debug_env("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
     if (const char* rg = vpu_debug_env("VPU_GEMM_RAGGED256")) g_ragged256 = rg[0] != '0';
+    if (const char* rk = vpu_debug_env("VPU_GEMM_RES_KMAX")) g_res_kmax = atoi(rk);
     if (const char* sm = vpu_debug_env("VPU_GEMM_SMALL_TILES")) g_small_tiles = sm[0] != '0';
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
@@ -1111,7 +1113,11 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         else
             VPU_REQUIRE(e.out_bf16 && !e.res && e.ln_s && (e.act == ACT_NONE || e.act == ACT_GELU),
                         "ln_in needs a bf16 output without residual and ln_s");
-        return ln_tile_bn(p.M, p.N) == 128 ? launch_tc2<128>(p, stream) : launch_tc2<256>(p, stream);
+        if (ln_tile_bn(p.M, p.N) == 128) return launch_tc2<128>(p, stream);
+        // HBM-bound residual GEMMs (K <= N: proj, 119 -> 92 us) take the TMA-staged epilogue of gemm_res.cu; fc2 (K = 4 N, tensor-bound)
+        // keeps the 5-stage ring of the generic kernel (186 us against 234 us with the 3-stage ring there)
+        if (e.ln_out && p.K <= p.N && p.K <= g_res_kmax && gemm_res_supported(p)) return gemm_res_launch(p, stream);
+        return launch_tc2<256>(p, stream);
     }
     if (impl == 1) {
 #ifndef VPU_DEBUG

@@ -84,6 +84,10 @@ int gemm_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes; idem
 int gemm_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int gemm_num_sms();
 
+// Residual-stream GEMM with a TMA-staged epilogue (gemm_res.cu): X (fp32, in place) += A W^T + bias, bf16 copy, LayerNorm slots
+bool gemm_res_supported(const GemmProblem& p);
+int gemm_res_launch(const GemmProblem& p, cudaStream_t stream);
+
 // Back-to-back GEMM pair of the segmentation head (gemm_b2b.cu): per pyramid level the 1x1 conv + ReLU and that level's
 // [256, 256] slice of the fusion conv (reference swin_transformer.py:723-737; the slice is applied at native resolution
 // because a 1x1 conv commutes with the bilinear resize),
