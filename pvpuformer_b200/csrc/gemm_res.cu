@@ -8,7 +8,7 @@
 //   * an epilogue thread (= accumulator row, straight out of TMEM) adds its staged residual row and the bias, writes the fp32
 //     result back in place and the bf16 copy into a second staging tile, and accumulates the row's sum / sum of squares,
 //   * the store warp sends fp32 and bf16 tiles back with TMA tensor stores and re-arms the staging pair with the next residual.
-// 2-CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles, 256 columns), two TMEM accumulators, a 3-stage operand ring.
+// 2-CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles, 256 columns), two TMEM accumulators, a 4-stage operand ring.
 // Statistics slots: one per (128-column group, column half of the 64-column pairs), computed in the generic epilogue's grouping
 // and order, so that both kernels -- the choice depends on M -- produce the same bits.
 #include "gemm.cuh"
@@ -21,7 +21,7 @@ namespace {
 constexpr int BM = 128, BK = 64, BN = 256;
 constexpr int CHUNK = BM * BK * 2;              // 16 KB operand tile: [128 rows x 64 bf16], 128-byte swizzle
 constexpr int STAGE = 2 * CHUNK;                // A k-chunk + B half k-chunk (128 of the tile's 256 weight rows)
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int UNIT = BM * 32 * 4;               // 16 KB: [128 rows x 32 fp32]
 constexpr int PAIR = 2 * UNIT + BM * 64 * 2;    // two fp32 units + one bf16 tile [128 x 64]: 48 KB
 constexpr int NPAIR = 2;
@@ -30,7 +30,7 @@ constexpr int SMEM = PAIR_OFF + NPAIR * PAIR + 1024;
 constexpr int EPI_WARPS = 8;
 constexpr int STORE_WARP = 2 + EPI_WARPS;
 constexpr int THREADS = (STORE_WARP + 1) * 32;
-static_assert(SMEM <= 232448 - 4096, "dynamic shared memory limit of sm_100");
+static_assert(SMEM <= 232448 - 1536, "dynamic shared memory limit of sm_100");
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -54,7 +54,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], res_full[NPAIR], pair_done[NPAIR];
-    __shared__ __align__(16) float bias_s[2][BN];
+    __shared__ __align__(16) float bias_s[BN];
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -151,8 +151,9 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int tile = pair; tile < tiles; tile += npairs, ++it) {
             const int m_blk = tile / n_blks, n_blk = tile % n_blks;
             const int m = m_blk * 2 * BM + rank * BM + row;
-            // this tile's 256 bias values (the previous tile's are still being read by slower warps: two buffers)
-            float* bs = bias_s[it & 1];
+            // this tile's 256 bias values: every epilogue warp has finished the previous tile (first barrier) before they are replaced
+            float* bs = bias_s;
+            asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
             if (warp == 2 || warp == 3) {
                 const int i = (warp - 2) * 128 + lane * 4;
                 *reinterpret_cast<float4*>(bs + i) = __ldg(reinterpret_cast<const float4*>(a.bias + n_blk * BN + i));
