@@ -1114,9 +1114,9 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
             VPU_REQUIRE(e.out_bf16 && !e.res && e.ln_s && (e.act == ACT_NONE || e.act == ACT_GELU),
                         "ln_in needs a bf16 output without residual and ln_s");
         if (ln_tile_bn(p.M, p.N) == 128) return launch_tc2<128>(p, stream);
-        // HBM-bound residual GEMMs (K <= N: proj, 119 -> 92 us) take the TMA-staged epilogue of gemm_res.cu; fc2 (K = 4 N, tensor-bound)
-        // keeps the 5-stage ring of the generic kernel (186 us against 234 us with the 3-stage ring there)
-        if (e.ln_out && p.K <= p.N && p.K <= g_res_kmax && gemm_res_supported(p)) return gemm_res_launch(p, stream);
+        // HBM-bound residual GEMMs (K <= 2 N: proj 119 -> 91 us, patch-embed low part) take the TMA-staged epilogue of gemm_res.cu; fc2
+        // (K = 4 N, tensor-bound) keeps the generic kernel (181 us against 188 us with a 5-stage / one-staging-pair variant there)
+        if (e.ln_out && p.K <= 2 * p.N && p.K <= g_res_kmax && gemm_res_supported(p)) return gemm_res_launch(p, stream);
         return launch_tc2<256>(p, stream);
     }
     if (impl == 1) {

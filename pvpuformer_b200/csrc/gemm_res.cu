@@ -21,16 +21,15 @@ namespace {
 constexpr int BM = 128, BK = 64, BN = 256;
 constexpr int CHUNK = BM * BK * 2;              // 16 KB operand tile: [128 rows x 64 bf16], 128-byte swizzle
 constexpr int STAGE = 2 * CHUNK;                // A k-chunk + B half k-chunk (128 of the tile's 256 weight rows)
-constexpr int STAGES = 4;
 constexpr int UNIT = BM * 32 * 4;               // 16 KB: [128 rows x 32 fp32]
 constexpr int PAIR = 2 * UNIT + BM * 64 * 2;    // two fp32 units + one bf16 tile [128 x 64]: 48 KB
-constexpr int NPAIR = 2;
-constexpr int RING_OFF = 0, PAIR_OFF = STAGES * STAGE;
-constexpr int SMEM = PAIR_OFF + NPAIR * PAIR + 1024;
+constexpr int RING_OFF = 0;
+// <STAGES, NPAIR> = <4, 2>: two staging pairs in flight and a 4-stage operand ring (3 stages starved the MMAs at K = 1280: 306 us
+// against 270).  <5, 1> was tried for the tensor-bound fc2 (K = 4 N): 188 us against 181 us for the generic kernel, not used.
+template <int STAGES, int NPAIR> __host__ __device__ constexpr int res_smem() { return STAGES * STAGE + NPAIR * PAIR + 1024; }
 constexpr int EPI_WARPS = 8;
 constexpr int STORE_WARP = 2 + EPI_WARPS;
 constexpr int THREADS = (STORE_WARP + 1) * 32;
-static_assert(SMEM <= 232448 - 1536, "dynamic shared memory limit of sm_100");
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -48,9 +47,12 @@ struct ResArgs {
     int M, N, K;
 };
 
+template <int STAGES, int NPAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ CUtensorMap tmXn, const ResArgs a) {
+    static_assert(res_smem<STAGES, NPAIR>() <= 232448 - 1536, "dynamic shared memory limit of sm_100");
+    constexpr int PAIR_OFF = STAGES * STAGE;
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], res_full[NPAIR], pair_done[NPAIR];
@@ -168,11 +170,11 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             float s8[8], q8[8];
 #pragma unroll 1
             for (int p = 0; p < 4; ++p, ++g) {
-                const int slot = g & 1;
+                const int slot = g % NPAIR;
                 uint8_t* ps = smem + PAIR_OFF + slot * PAIR;
                 uint32_t r[32];
                 tmem_ld_32x32(t_acc + p * 64, r);
-                mbar_wait(&res_full[slot], (uint32_t)((g >> 1) & 1));      // both fp32 residual units of this pair have landed
+                mbar_wait(&res_full[slot], (uint32_t)((g / NPAIR) & 1));      // both fp32 residual units of this pair have landed
                 tmem_ld_wait();
                 if (p == 3) {                        // the accumulator is in registers: the MMAs of the tile after next may overwrite it
                     tc_fence_before();
@@ -229,28 +231,29 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         auto load_res = [&](int g) {
             int row0, col0;
             coords(g, row0, col0);
-            uint8_t* ps = smem + PAIR_OFF + (g & 1) * PAIR;
-            mbar_arrive_expect_tx(&res_full[g & 1], 2 * UNIT);
-            tma_load_2d(ps, &tmX, &res_full[g & 1], col0, row0);
-            tma_load_2d(ps + UNIT, &tmX, &res_full[g & 1], col0 + 32, row0);
+            uint8_t* ps = smem + PAIR_OFF + (g % NPAIR) * PAIR;
+            mbar_arrive_expect_tx(&res_full[g % NPAIR], 2 * UNIT);
+            tma_load_2d(ps, &tmX, &res_full[g % NPAIR], col0, row0);
+            tma_load_2d(ps + UNIT, &tmX, &res_full[g % NPAIR], col0 + 32, row0);
         };
         if (elect_one()) {
-            if (npairs_total > 0) load_res(0);
-            if (npairs_total > 1) load_res(1);
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i)
+                if (npairs_total > i) load_res(i);
         }
         __syncwarp();
         for (int g = 0; g < npairs_total; ++g) {
-            mbar_wait(&pair_done[g & 1], (uint32_t)((g >> 1) & 1));
+            mbar_wait(&pair_done[g % NPAIR], (uint32_t)((g / NPAIR) & 1));
             if (elect_one()) {
                 int row0, col0;
                 coords(g, row0, col0);
-                uint8_t* ps = smem + PAIR_OFF + (g & 1) * PAIR;
+                uint8_t* ps = smem + PAIR_OFF + (g % NPAIR) * PAIR;
                 tma_store_2d(&tmX, ps, col0, row0);
                 tma_store_2d(&tmX, ps + UNIT, col0 + 32, row0);
                 tma_store_2d(&tmXn, ps + 2 * UNIT, col0, row0);
                 tma_store_commit();
                 tma_store_wait_read();
-                if (g + 2 < npairs_total) load_res(g + 2);
+                if (g + NPAIR < npairs_total) load_res(g + NPAIR);
             }
             __syncwarp();
         }
@@ -297,17 +300,17 @@ bool gemm_res_supported(const GemmProblem& p) {
            (reinterpret_cast<uintptr_t>(e.ln_out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
 }
 
-int gemm_res_launch(const GemmProblem& p, cudaStream_t stream) {
-    if (int rc = gemm_init()) return rc;
-    VPU_REQUIRE(gemm_res_supported(p), "residual GEMM: unsupported problem");
+template <int STAGES, int NPAIR>
+static int launch_res(const GemmProblem& p, cudaStream_t stream) {
     CUtensorMap tmA, tmW, tmX, tmXn;
     if (int rc = gemm_tmap(&tmA, p.A, p.M, p.K, p.lda, BM)) return rc;
     if (int rc = gemm_tmap(&tmW, p.W, p.N, p.K, p.ldw, BM)) return rc;
     if (int rc = make_map(&tmX, p.epi.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.M, p.N, p.epi.ldo, 32)) return rc;
     if (int rc = make_map(&tmXn, p.epi.ln_out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.M, p.N, p.epi.ldo, 64)) return rc;
+    constexpr int SMEM = res_smem<STAGES, NPAIR>();
     static bool attr_set = false;
     if (!attr_set) {
-        VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_res_kernel<STAGES, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
@@ -323,15 +326,21 @@ int gemm_res_launch(const GemmProblem& p, cudaStream_t stream) {
     if (max_clusters == 0) {
         cfg.gridDim = dim3(2 * (gemm_num_sms() / 2));
         int n = 0;
-        VPU_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_res_kernel, &cfg));
+        VPU_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_res_kernel<STAGES, NPAIR>, &cfg));
         max_clusters = n > 0 ? n : 1;
     }
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
     cfg.gridDim = dim3(2 * clusters);
     ResArgs a{p.epi.bias, p.epi.ln_out, p.epi.ln_slots, p.M, p.N, p.K};
-    VPU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_res_kernel, tmA, tmW, tmX, tmXn, a));
+    VPU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_res_kernel<STAGES, NPAIR>, tmA, tmW, tmX, tmXn, a));
     count_launch();
     return 0;
+}
+
+int gemm_res_launch(const GemmProblem& p, cudaStream_t stream) {
+    if (int rc = gemm_init()) return rc;
+    VPU_REQUIRE(gemm_res_supported(p), "residual GEMM: unsupported problem");
+    return launch_res<4, 2>(p, stream);
 }
 
 }  // namespace vpu
