@@ -881,6 +881,7 @@ static int g_stages = 0;
 static int g_cluster = 2;
 static int g_ablate = 0;
 static bool g_ragged256 = true;
+static int g_gn_tma = 1;                // VPU_GEMM_GN_TMA (-DVPU_DEBUG builds): 0 keeps the GroupNorm-fused neck GEMMs on the generic epilogue
 static int g_res_kmax = 1 << 30;       // VPU_GEMM_RES_KMAX (-DVPU_DEBUG builds): largest K that takes gemm_res.cu (0 = never)
 static std::mutex g_mu;
 
@@ -960,6 +961,7 @@ int gemm_init() {
     if (const char* ab = vpu_debug_env("VPU_GEMM_ABLATE")) g_ablate = atoi(ab);
     if (const char* rg = vpu_debug_env("VPU_GEMM_RAGGED256")) g_ragged256 = rg[0] != '0';
     if (const char* rk = vpu_debug_env("VPU_GEMM_RES_KMAX")) g_res_kmax = atoi(rk);
+    if (const char* gt = vpu_debug_env("VPU_GEMM_GN_TMA")) g_gn_tma = atoi(gt);
     if (const char* sm = vpu_debug_env("VPU_GEMM_SMALL_TILES")) g_small_tiles = sm[0] != '0';
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
@@ -1119,6 +1121,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         if (e.ln_out && p.K <= 2 * p.N && p.K <= g_res_kmax && gemm_res_supported(p)) return gemm_res_launch(p, stream);
         return launch_tc2<256>(p, stream);
     }
+    // HBM-bound GroupNorm-fused neck GEMMs (K < 2 N, bf16 output + statistics): TMA-staged epilogue of gemm_gn.cu, same bits
+    if (impl == 0 && g_use_2cta && g_gn_tma && gemm_gn_supported(p)) return gemm_gn_launch(p, stream);
     if (impl == 1) {
 #ifndef VPU_DEBUG
         VPU_REQUIRE(false, "GEMM impl 1 (mma.sync cross-check) exists in -DVPU_DEBUG builds only");

@@ -87,6 +87,9 @@ int gemm_num_sms();
 // Residual-stream GEMM with a TMA-staged epilogue (gemm_res.cu): X (fp32, in place) += A W^T + bias, bf16 copy, LayerNorm slots
 bool gemm_res_supported(const GemmProblem& p);
 int gemm_res_launch(const GemmProblem& p, cudaStream_t stream);
+// GroupNorm-fused neck GEMM with a TMA-staged epilogue (gemm_gn.cu): bf16 out = [rstd (A W^T) - mean rstd wg] + bias, int64 statistics
+bool gemm_gn_supported(const GemmProblem& p);
+int gemm_gn_launch(const GemmProblem& p, cudaStream_t stream);
 
 // Back-to-back GEMM pair of the segmentation head (gemm_b2b.cu): per pyramid level the 1x1 conv + ReLU and that level's
 // [256, 256] slice of the fusion conv (reference swin_transformer.py:723-737; the slice is applied at native resolution

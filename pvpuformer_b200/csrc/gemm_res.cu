@@ -150,17 +150,20 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int acc = 0, it = 0;
         uint32_t acc_phase = 0;
         int g = 0;                                   // running 64-column pair index of this CTA: staging slot g & 1, phase (g >> 1) & 1
+        float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((warp == 2 || warp == 3) && pair < tiles)
+            bias_next = __ldg(reinterpret_cast<const float4*>(a.bias + (pair % n_blks) * BN + (warp - 2) * 128 + lane * 4));
         for (int tile = pair; tile < tiles; tile += npairs, ++it) {
             const int m_blk = tile / n_blks, n_blk = tile % n_blks;
             const int m = m_blk * 2 * BM + rank * BM + row;
             // this tile's 256 bias values: every epilogue warp has finished the previous tile (first barrier) before they are replaced
+            // (the values were requested one tile earlier: no global-memory latency between the two barriers)
             float* bs = bias_s;
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-            if (warp == 2 || warp == 3) {
-                const int i = (warp - 2) * 128 + lane * 4;
-                *reinterpret_cast<float4*>(bs + i) = __ldg(reinterpret_cast<const float4*>(a.bias + n_blk * BN + i));
-            }
+            if (warp == 2 || warp == 3) *reinterpret_cast<float4*>(bs + (warp - 2) * 128 + lane * 4) = bias_next;
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+            if ((warp == 2 || warp == 3) && tile + npairs < tiles)
+                bias_next = __ldg(reinterpret_cast<const float4*>(a.bias + ((tile + npairs) % n_blks) * BN + (warp - 2) * 128 + lane * 4));
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 32;
