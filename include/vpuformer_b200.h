@@ -122,6 +122,11 @@ int vpu_head_tail(const void* y0_bf16, const void* y1_bf16, const void* y2_bf16,
  * out[M,256] = bf16( bf16(relu(A[M,K1] * W1[256,K1]^T + bias1)) * W2[256,256]^T ) */
 int vpu_gemm_b2b(const void* A_bf16, int lda, const void* W1_bf16, const float* bias1, const void* W2_bf16, int M, int K1,
                  void* out_bf16, int ldo, void* stream);
+/* image-side K|V|Q projection of the Dual-cross Merging Attention (reference transformer.py:444-449, 456-458): the positional term
+ * key_pe W^T + b is a precomputed fp32 table of table_rows + table_pad_rows rows, the first table_pad_rows (>= 128) repeated after the
+ * last one.  out[M,N] (bf16) = A[M,K] * W[N,K]^T + table[m % table_rows, N] */
+int vpu_gemm_table(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* table, int table_rows,
+                   int table_pad_rows, void* out_bf16, int ldo, int impl, void* stream);
 /* ConvTranspose2d(k=2,s=2) as GEMM + pixel-shuffle store: A [B*g*g, K] -> out NHWC [B, 2g, 2g, cout] bf16 */
 int vpu_gemm_pixel_shuffle(const void* A_bf16, const void* W_bf16, int M, int cout, int K, const float* bias4, int g,
                            void* out_bf16, int impl, void* stream);

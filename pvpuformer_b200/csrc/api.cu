@@ -108,6 +108,8 @@ struct vpu_context {
 
 namespace {
 
+constexpr int TAB_PAD = 128;   // packing.py TAB_PAD: rows the positional tables repeat after their last row (gemm_res.cu MODE_TAB)
+
 Plan make_plan(const vpu_context& h, int B) {
     Plan p;
     const size_t C = h.C(), N = h.N(), M = (size_t)B * N, Q = h.Q(), MQ = (size_t)B * Q, g = h.grid();
@@ -244,13 +246,13 @@ struct Fwd {
     // out = act(A W^T + bias [+ tab] [+ res])
     int gemm(const __nv_bfloat16* A, int lda, const std::string& wkey, int M, int Nn, int K, const float* bias, void* out,
              bool out_bf16, int ldo, int act = ACT_NONE, const void* res = nullptr, bool res_bf16 = false, int ldr = 0,
-             const float* tab = nullptr, int tab_rows = 0, const Gn* gn = nullptr, const Ln* ln = nullptr) {
+             const float* tab = nullptr, int tab_rows = 0, const Gn* gn = nullptr, const Ln* ln = nullptr, int tab_pad = 0) {
         GemmProblem p;
         p.A = A; p.W = Wb(wkey); p.M = M; p.N = Nn; p.K = K; p.lda = lda;
         p.ldw = (int)h.w.at(wkey).shape[1];
         p.w_rows = Nn;
         p.epi.out = out; p.epi.out_bf16 = out_bf16; p.epi.ldo = ldo; p.epi.bias = bias; p.epi.act = act;
-        p.epi.res = res; p.epi.res_bf16 = res_bf16; p.epi.ldr = ldr; p.epi.bias2d = tab; p.epi.bias2d_rows = tab_rows;
+        p.epi.res = res; p.epi.res_bf16 = res_bf16; p.epi.ldr = ldr; p.epi.bias2d = tab; p.epi.bias2d_rows = tab_rows; p.epi.bias2d_pad_rows = tab_pad;
         if (gn) set_gn(p.epi, *gn);
         if (ln) {
             p.epi.ln_out = ln->out; p.epi.ln_out_bf16 = ln->out_bf16; p.epi.ln_in = ln->in; p.epi.ln_s = ln->s;
@@ -469,7 +471,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         //     positional term key_pe W^T is a precomputed additive table (transformer.py:444-449)
         RUN(f.gemm(QPb, C, k + ".t2i.q.w", MQ, Ci, C, f.Wf(k + ".t2i.q.b"), f.buf<bf>("TQ"), true, Ci));
         RUN(f.gemm(Kin, C, k + ".img.w", M, 3 * Ci, C, nullptr, KVQ, true, 3 * Ci, ACT_NONE, nullptr, false, 0,
-                   f.Wf(k + ".img.tab"), N));
+                   f.Wf(k + ".img.tab"), N, nullptr, nullptr, TAB_PAD));
         RUN(f.attn(f.buf<bf>("TQ"), Ci, 0, KVQ, 3 * Ci, 0, KVQ, 3 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
                    1.0f / sqrtf((float)dcross), false));
         RUN(f.gemm(f.buf<bf>("TO"), Ci, k + ".t2i.o.w", MQ, C, Ci, f.Wf(k + ".t2i.o.b"), T, false, C, ACT_NONE, Qf, false, C));
@@ -494,7 +496,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     // final tokens -> image attention (transformer.py:374-379)
     RUN(f.gemm(QPb, C, "dmaf.q.w", MQ, Ci, C, f.Wf("dmaf.q.b"), f.buf<bf>("TQ"), true, Ci));
     RUN(f.gemm(Kin, C, "dmaf.img.w", M, 2 * Ci, C, nullptr, KVQ, true, 2 * Ci, ACT_NONE, nullptr, false, 0,
-               f.Wf("dmaf.img.tab"), N));
+               f.Wf("dmaf.img.tab"), N, nullptr, nullptr, TAB_PAD));
     RUN(f.attn(f.buf<bf>("TQ"), Ci, 0, KVQ, 2 * Ci, 0, KVQ, 2 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
                1.0f / sqrtf((float)dcross), false));
     RUN(f.gemm(f.buf<bf>("TO"), Ci, "dmaf.o.w", MQ, C, Ci, f.Wf("dmaf.o.b"), T, false, C, ACT_NONE, Qf, false, C));
@@ -666,14 +668,14 @@ std::vector<Need> needed_weights(const vpu_context& h) {
         lin(k + ".sa.qk", 2 * C, C); lin(k + ".sa.v", C, C); lin(k + ".sa.o", C, C); nrm(k + ".n1", C);
         lin(k + ".t2i.q", Ci, C);
         v.push_back({k + ".img.w", VPU_BF16, {3 * Ci, C}});
-        v.push_back({k + ".img.tab", VPU_F32, {N, 3 * Ci}});
+        v.push_back({k + ".img.tab", VPU_F32, {N + TAB_PAD, 3 * Ci}});   // rows 0 .. TAB_PAD-1 repeated at the end
         lin(k + ".t2i.o", C, Ci); nrm(k + ".n2", C);
         lin2(k + ".mlp", "1", h.d.dma_mlp_dim, C); lin2(k + ".mlp", "2", C, h.d.dma_mlp_dim); nrm(k + ".n3", C);
         lin(k + ".i2t.k", Ci, C); lin(k + ".i2t.v", Ci, C); lin(k + ".i2t.o", C, Ci); nrm(k + ".n4", C);
     }
     lin("dmaf.q", Ci, C);
     v.push_back({"dmaf.img.w", VPU_BF16, {2 * Ci, C}});
-    v.push_back({"dmaf.img.tab", VPU_F32, {N, 2 * Ci}});
+    v.push_back({"dmaf.img.tab", VPU_F32, {N + TAB_PAD, 2 * Ci}});
     lin("dmaf.o", C, Ci); nrm("dmaf.n", C);
     const int64_t d4 = h.d4(), d8 = h.d8(), d32 = h.d32();
     const int* od = h.d.out_dims;
@@ -886,6 +888,17 @@ int vpu_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K
     p.epi.out = out; p.epi.out_bf16 = out_dtype == VPU_BF16; p.epi.ldo = ldo; p.epi.bias = bias; p.epi.bias2d = bias2d;
     p.epi.bias2d_rows = bias2d_rows; p.epi.res = residual; p.epi.res_bf16 = residual_dtype == VPU_BF16; p.epi.ldr = ldr;
     p.epi.act = act;
+    return gemm_launch(p, reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int vpu_gemm_table(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* table, int table_rows,
+                   int table_pad_rows, void* out, int ldo, int impl, void* stream) {
+    VPU_REQUIRE(A && W && out && table && table_rows > 0 && table_pad_rows >= 0, "vpu_gemm_table: bad argument");
+    GemmProblem p;
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A); p.W = reinterpret_cast<const __nv_bfloat16*>(W);
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.w_rows = N;
+    p.epi.out = out; p.epi.out_bf16 = 1; p.epi.ldo = ldo; p.epi.bias2d = table; p.epi.bias2d_rows = table_rows;
+    p.epi.bias2d_pad_rows = table_pad_rows;
     return gemm_launch(p, reinterpret_cast<cudaStream_t>(stream), impl);
 }
 

@@ -841,7 +841,8 @@ int gemm_ln_slots(int, int N) { return ((N + 127) / 128) * EpiWarps<EK_F32_RES_L
 int gemm_ln_slots_max(int N) { return ((N + 127) / 128) * EpiWarps<EK_F32_RES_LNOUT>::N; }
 
 // Row statistics of the LayerNorm fusion: the slots a residual GEMM wrote (Epi::ln_out) -> (rstd, mean * rstd) per row, added in
-// slot order in double precision (one thread per row; 2.4 MB in, 0.4 MB out for ViT-B at batch 64).
+// slot order in double precision (one thread per row; 2.4 MB in, 0.4 MB out for ViT-B at batch 64; eight lanes per row with
+// coalesced slot reads measured the same 8-9 us under the event brackets: the launch is latency, not traffic).
 __global__ void __launch_bounds__(256) ln_rowstats_kernel(const float2* __restrict__ slots, int M, int P, float inv_c, float eps,
                                                           float2* __restrict__ out) {
     pdl_launch_dependents();
@@ -882,6 +883,7 @@ static int g_cluster = 2;
 static int g_ablate = 0;
 static bool g_ragged256 = true;
 static int g_gn_tma = 1;                // VPU_GEMM_GN_TMA (-DVPU_DEBUG builds): 0 keeps the GroupNorm-fused neck GEMMs on the generic epilogue
+static int g_res_modes = 1;             // VPU_GEMM_RES_MODES (-DVPU_DEBUG builds): 0 keeps the table GEMMs on the generic epilogue
 static int g_res_kmax = 1 << 30;       // VPU_GEMM_RES_KMAX (-DVPU_DEBUG builds): largest K that takes gemm_res.cu (0 = never)
 static std::mutex g_mu;
 
@@ -962,6 +964,7 @@ int gemm_init() {
     if (const char* rg = vpu_debug_env("VPU_GEMM_RAGGED256")) g_ragged256 = rg[0] != '0';
     if (const char* rk = vpu_debug_env("VPU_GEMM_RES_KMAX")) g_res_kmax = atoi(rk);
     if (const char* gt = vpu_debug_env("VPU_GEMM_GN_TMA")) g_gn_tma = atoi(gt);
+    if (const char* rm = vpu_debug_env("VPU_GEMM_RES_MODES")) g_res_modes = atoi(rm);
     if (const char* sm = vpu_debug_env("VPU_GEMM_SMALL_TILES")) g_small_tiles = sm[0] != '0';
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
@@ -1123,6 +1126,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
     }
     // HBM-bound GroupNorm-fused neck GEMMs (K < 2 N, bf16 output + statistics): TMA-staged epilogue of gemm_gn.cu, same bits
     if (impl == 0 && g_use_2cta && g_gn_tma && gemm_gn_supported(p)) return gemm_gn_launch(p, stream);
+    // the DMA stage's image-side K|V|Q projections: positional table through the TMA-staged epilogue of gemm_res.cu
+    if (impl == 0 && g_use_2cta && g_res_modes && gemm_tab_supported(p)) return gemm_tab_launch(p, stream);
     if (impl == 1) {
 #ifndef VPU_DEBUG
         VPU_REQUIRE(false, "GEMM impl 1 (mma.sync cross-check) exists in -DVPU_DEBUG builds only");

@@ -19,6 +19,7 @@ struct Epi {
     const float* bias = nullptr;    // [N]
     const float* bias2d = nullptr;  // [bias2d_rows, N], row = m % bias2d_rows (positional tables)
     int bias2d_rows = 0;
+    int bias2d_pad_rows = 0;        // rows 0 .. pad-1 of the table are repeated after row bias2d_rows-1 (a 128-row TMA box never wraps)
     const void* res = nullptr;      // residual [M, ldr], fp32 or bf16, added before the activation is NOT
     int res_bf16 = 0;               //   applied (act and res are never combined on this path)
     int ldr = 0;
@@ -87,6 +88,9 @@ int gemm_num_sms();
 // Residual-stream GEMM with a TMA-staged epilogue (gemm_res.cu): X (fp32, in place) += A W^T + bias, bf16 copy, LayerNorm slots
 bool gemm_res_supported(const GemmProblem& p);
 int gemm_res_launch(const GemmProblem& p, cudaStream_t stream);
+// same skeleton: bf16 out = A W^T + periodic fp32 table (needs Epi::bias2d_pad_rows >= 128)
+bool gemm_tab_supported(const GemmProblem& p);
+int gemm_tab_launch(const GemmProblem& p, cudaStream_t stream);
 // GroupNorm-fused neck GEMM with a TMA-staged epilogue (gemm_gn.cu): bf16 out = [rstd (A W^T) - mean rstd wg] + bias, int64 statistics
 bool gemm_gn_supported(const GemmProblem& p);
 int gemm_gn_launch(const GemmProblem& p, cudaStream_t stream);

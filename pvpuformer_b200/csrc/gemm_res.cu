@@ -11,6 +11,12 @@
 // 2-CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles, 256 columns), two TMEM accumulators, a 4-stage operand ring.
 // Statistics slots: one per (128-column group, column half of the 64-column pairs), computed in the generic epilogue's grouping
 // and order, so that both kernels -- the choice depends on M -- produce the same bits.
+// A second mode shares the skeleton (Dual-cross Merging Attention, image side, reference transformer.py:444-449, 456-458):
+//   MODE_TAB    out (bf16) = A W^T + table[m mod R]      the fused K|V|Q projection of the image tokens, whose positional term
+//               key_pe W^T + b is a precomputed fp32 table (R + 128 rows: the first 128 repeated, so one box never wraps);
+//               106 -> 87 us at 50176 x 1152 x 768.  (A third mode for the image -> tokens out-projection, fp32 out = A W^T +
+//               bias + bf16 residual with the residual tile loaded by TMA, measured 59.9 against 59.6 us for the generic epilogue
+//               and was removed.)
 #include "gemm.cuh"
 #include "tc_attn.cuh"
 
@@ -45,9 +51,13 @@ struct ResArgs {
     float2* ln_out;
     int ln_slots;
     int M, N, K;
+    int tab_rows;                 // MODE_TAB: period R of the table
 };
+enum { MODE_RES = 0, MODE_TAB = 1 };
 
-template <int STAGES, int NPAIR>
+// tmX: fp32 [*, N] in boxes of 32 columns (MODE_RES: residual stream in / out; MODE_TAB: the table);
+// tmXn: bf16 [M, N] in boxes of 64 columns (MODE_RES: bf16 copy; MODE_TAB: the output)
+template <int STAGES, int NPAIR, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ CUtensorMap tmXn, const ResArgs a) {
@@ -91,7 +101,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = tmem_base_smem;
     pdl_wait();
 
-    const int n_blks = a.N / BN;
+    const int n_blks = (a.N + BN - 1) / BN;         // MODE_TAB: N = 1152 leaves a half tile (TMA zero-fills the loads and clips the stores)
     const int m_blks = (a.M + 2 * BM - 1) / (2 * BM);
     const int tiles = n_blks * m_blks;
     const int kblks = (a.K + BK - 1) / BK;
@@ -151,7 +161,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t acc_phase = 0;
         int g = 0;                                   // running 64-column pair index of this CTA: staging slot g & 1, phase (g >> 1) & 1
         float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((warp == 2 || warp == 3) && pair < tiles)
+        if (MODE == MODE_RES && (warp == 2 || warp == 3) && pair < tiles)
             bias_next = __ldg(reinterpret_cast<const float4*>(a.bias + (pair % n_blks) * BN + (warp - 2) * 128 + lane * 4));
         for (int tile = pair; tile < tiles; tile += npairs, ++it) {
             const int m_blk = tile / n_blks, n_blk = tile % n_blks;
@@ -162,7 +172,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
             if (warp == 2 || warp == 3) *reinterpret_cast<float4*>(bs + (warp - 2) * 128 + lane * 4) = bias_next;
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-            if ((warp == 2 || warp == 3) && tile + npairs < tiles)
+            if (MODE == MODE_RES && (warp == 2 || warp == 3) && tile + npairs < tiles)
                 bias_next = __ldg(reinterpret_cast<const float4*>(a.bias + ((tile + npairs) % n_blks) * BN + (warp - 2) * 128 + lane * 4));
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
@@ -187,30 +197,43 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 uint8_t* frow = ps + half * UNIT + row * 128;
                 uint8_t* brow = ps + 2 * UNIT + row * 128;
                 const float* bb = bs + p * 64 + half * 32;
-                uint32_t pk[16];
+                if constexpr (MODE == MODE_RES) {
+                    uint32_t pk[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    float4* q = reinterpret_cast<float4*>(frow + ((u ^ sw) << 4));
-                    float4 x = *q;
-                    const float4 bv = *reinterpret_cast<const float4*>(bb + 4 * u);
-                    x.x += __uint_as_float(r[4 * u]) + bv.x;
-                    x.y += __uint_as_float(r[4 * u + 1]) + bv.y;
-                    x.z += __uint_as_float(r[4 * u + 2]) + bv.z;
-                    x.w += __uint_as_float(r[4 * u + 3]) + bv.w;
-                    *q = x;
-                    const float ps_ = (x.x + x.y) + (x.z + x.w), pq_ = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
-                    s8[u] = (p & 1) ? s8[u] + ps_ : ps_;
-                    q8[u] = (p & 1) ? q8[u] + pq_ : pq_;
-                    pk[2 * u] = pack_bf16(x.x, x.y);
-                    pk[2 * u + 1] = pack_bf16(x.z, x.w);
+                    for (int u = 0; u < 8; ++u) {
+                        float4* q = reinterpret_cast<float4*>(frow + ((u ^ sw) << 4));
+                        float4 x = *q;
+                        const float4 bv = *reinterpret_cast<const float4*>(bb + 4 * u);
+                        x.x += __uint_as_float(r[4 * u]) + bv.x;
+                        x.y += __uint_as_float(r[4 * u + 1]) + bv.y;
+                        x.z += __uint_as_float(r[4 * u + 2]) + bv.z;
+                        x.w += __uint_as_float(r[4 * u + 3]) + bv.w;
+                        *q = x;
+                        const float ps_ = (x.x + x.y) + (x.z + x.w), pq_ = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+                        s8[u] = (p & 1) ? s8[u] + ps_ : ps_;
+                        q8[u] = (p & 1) ? q8[u] + pq_ : pq_;
+                        pk[2 * u] = pack_bf16(x.x, x.y);
+                        pk[2 * u + 1] = pack_bf16(x.z, x.w);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(brow + (((4 * half + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                } else if constexpr (MODE == MODE_TAB) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 x = *reinterpret_cast<const float4*>(frow + ((u ^ sw) << 4));     // table row (accumulator + table: the generic order)
+                        pk[2 * u] = pack_bf16(__uint_as_float(r[4 * u]) + x.x, __uint_as_float(r[4 * u + 1]) + x.y);
+                        pk[2 * u + 1] = pack_bf16(__uint_as_float(r[4 * u + 2]) + x.z, __uint_as_float(r[4 * u + 3]) + x.w);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(brow + (((4 * half + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    *reinterpret_cast<uint4*>(brow + (((4 * half + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pair_done[slot]);
-                if (p & 1) {                         // a 128-column group of the row is complete: its slot
+                if (MODE == MODE_RES && (p & 1)) {   // a 128-column group of the row is complete: its slot
                     const float sum = ((s8[0] + s8[4]) + (s8[2] + s8[6])) + ((s8[1] + s8[5]) + (s8[3] + s8[7]));
                     const float sq = ((q8[0] + q8[4]) + (q8[2] + q8[6])) + ((q8[1] + q8[5]) + (q8[3] + q8[7]));
                     if (m < a.M) a.ln_out[(size_t)m * a.ln_slots + (n_blk * 2 + (p >> 1)) * 2 + half] = make_float2(sum, sq);
@@ -235,6 +258,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int row0, col0;
             coords(g, row0, col0);
             uint8_t* ps = smem + PAIR_OFF + (g % NPAIR) * PAIR;
+            if constexpr (MODE == MODE_TAB) row0 %= a.tab_rows;
             mbar_arrive_expect_tx(&res_full[g % NPAIR], 2 * UNIT);
             tma_load_2d(ps, &tmX, &res_full[g % NPAIR], col0, row0);
             tma_load_2d(ps + UNIT, &tmX, &res_full[g % NPAIR], col0 + 32, row0);
@@ -251,8 +275,10 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 int row0, col0;
                 coords(g, row0, col0);
                 uint8_t* ps = smem + PAIR_OFF + (g % NPAIR) * PAIR;
-                tma_store_2d(&tmX, ps, col0, row0);
-                tma_store_2d(&tmX, ps + UNIT, col0 + 32, row0);
+                if constexpr (MODE == MODE_RES) {
+                    tma_store_2d(&tmX, ps, col0, row0);
+                    tma_store_2d(&tmX, ps + UNIT, col0 + 32, row0);
+                }
                 tma_store_2d(&tmXn, ps + 2 * UNIT, col0, row0);
                 tma_store_commit();
                 tma_store_wait_read();
@@ -303,20 +329,38 @@ bool gemm_res_supported(const GemmProblem& p) {
            (reinterpret_cast<uintptr_t>(e.ln_out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
 }
 
-template <int STAGES, int NPAIR>
+static bool plain_epilogue(const Epi& e) {
+    return e.mode == EPI_PLAIN && e.act == ACT_NONE && !e.ln_out && !e.ln_in && !e.gn_in && !e.gn_out && e.out;
+}
+
+// out (bf16) = A W^T + table[m mod R]; the table holds R + 128 rows (Epi::bias2d_pad_rows)
+bool gemm_tab_supported(const GemmProblem& p) {
+    const Epi& e = p.epi;
+    return plain_epilogue(e) && e.bias2d && e.bias2d_rows > 0 && e.bias2d_pad_rows >= BM && e.out_bf16 && !e.bias && !e.res && p.N % 64 == 0 &&
+           p.K % 8 == 0 && p.K <= 2 * p.N && p.M >= 2 * BM && e.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(e.bias2d) & 15) == 0;
+}
+
+template <int STAGES, int NPAIR, int MODE>
 static int launch_res(const GemmProblem& p, cudaStream_t stream) {
+    const Epi& e = p.epi;
     CUtensorMap tmA, tmW, tmX, tmXn;
     if (int rc = gemm_tmap(&tmA, p.A, p.M, p.K, p.lda, BM)) return rc;
     if (int rc = gemm_tmap(&tmW, p.W, p.N, p.K, p.ldw, BM)) return rc;
-    if (int rc = make_map(&tmX, p.epi.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.M, p.N, p.epi.ldo, 32)) return rc;
-    if (int rc = make_map(&tmXn, p.epi.ln_out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.M, p.N, p.epi.ldo, 64)) return rc;
+    if (MODE == MODE_RES) {
+        if (int rc = make_map(&tmX, e.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.M, p.N, e.ldo, 32)) return rc;
+        if (int rc = make_map(&tmXn, e.ln_out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.M, p.N, e.ldo, 64)) return rc;
+    } else {
+        if (int rc = make_map(&tmX, e.bias2d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.bias2d_rows + e.bias2d_pad_rows, p.N, p.N, 32)) return rc;
+        if (int rc = make_map(&tmXn, e.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.M, p.N, e.ldo, 64)) return rc;
+    }
     constexpr int SMEM = res_smem<STAGES, NPAIR>();
     static bool attr_set = false;
     if (!attr_set) {
-        VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_res_kernel<STAGES, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        VPU_CHECK_CUDA(cudaFuncSetAttribute(gemm_res_kernel<STAGES, NPAIR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
-    const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
+    const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -329,13 +373,13 @@ static int launch_res(const GemmProblem& p, cudaStream_t stream) {
     if (max_clusters == 0) {
         cfg.gridDim = dim3(2 * (gemm_num_sms() / 2));
         int n = 0;
-        VPU_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_res_kernel<STAGES, NPAIR>, &cfg));
+        VPU_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_res_kernel<STAGES, NPAIR, MODE>, &cfg));
         max_clusters = n > 0 ? n : 1;
     }
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
     cfg.gridDim = dim3(2 * clusters);
-    ResArgs a{p.epi.bias, p.epi.ln_out, p.epi.ln_slots, p.M, p.N, p.K};
-    VPU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_res_kernel<STAGES, NPAIR>, tmA, tmW, tmX, tmXn, a));
+    ResArgs a{e.bias, e.ln_out, e.ln_slots, p.M, p.N, p.K, e.bias2d_rows};
+    VPU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_res_kernel<STAGES, NPAIR, MODE>, tmA, tmW, tmX, tmXn, a));
     count_launch();
     return 0;
 }
@@ -343,7 +387,13 @@ static int launch_res(const GemmProblem& p, cudaStream_t stream) {
 int gemm_res_launch(const GemmProblem& p, cudaStream_t stream) {
     if (int rc = gemm_init()) return rc;
     VPU_REQUIRE(gemm_res_supported(p), "residual GEMM: unsupported problem");
-    return launch_res<4, 2>(p, stream);
+    return launch_res<4, 2, MODE_RES>(p, stream);
+}
+
+int gemm_tab_launch(const GemmProblem& p, cudaStream_t stream) {
+    if (int rc = gemm_init()) return rc;
+    VPU_REQUIRE(gemm_tab_supported(p), "table GEMM: unsupported problem");
+    return launch_res<4, 2, MODE_TAB>(p, stream);
 }
 
 }  // namespace vpu

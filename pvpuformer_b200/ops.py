@@ -27,6 +27,16 @@ def gemm(A, W, bias=None, bias2d=None, residual=None, act=None, out_dtype=torch.
     return out
 
 
+def gemm_table(A, W, table, table_rows, impl=0):
+    """bf16(A @ W.T + table[m % table_rows]); table: fp32 [table_rows + pad, N] with its first `pad` rows repeated at the end."""
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
+    L.check(L.load().vpu_gemm_table(L.ptr(A), A.stride(0), L.ptr(W), W.stride(0), M, N, K, L.ptr(table), table_rows,
+                                    table.shape[0] - table_rows, L.ptr(out), out.stride(0), impl, L.current_stream()))
+    return out
+
+
 def gemm_b2b(A, W1, bias1, W2):
     """bf16( bf16(relu(A @ W1.T + bias1)) @ W2.T ): the head's conv + ReLU + fusion-conv slice of one pyramid level."""
     M, K1 = A.shape

@@ -39,6 +39,15 @@ def key_pe_table(C, g, device):
     return pe.reshape(C, g * g).t().contiguous()
 
 
+TAB_PAD = 128   # api.cu TAB_PAD: the positional tables of the image-side projections repeat their first rows after the last one,
+                # so that a 128-row TMA box starting at row (m mod N) never wraps (gemm_res.cu MODE_TAB)
+
+
+def _pad_table(t):
+    reps = (TAB_PAD + t.shape[0] - 1) // t.shape[0] + 1
+    return torch.cat([t] * reps, 0)[: t.shape[0] + TAB_PAD].contiguous()
+
+
 def pack_weights(sd, cfg, device):
     """-> (dict key -> device tensor (bf16 or fp32, contiguous), dict scalar key -> float)."""
     f = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in sd.items()}
@@ -128,7 +137,7 @@ def pack_weights(sd, cfg, device):
         tabk = kpe @ f[t2i + ".k_proj.weight"].t() + f[t2i + ".k_proj.bias"]
         tabv = f[t2i + ".v_proj.bias"].view(1, Ci).expand(N, Ci)
         tabq = kpe @ f[i2t + ".q_proj.weight"].t() + f[i2t + ".q_proj.bias"]
-        F32(d + ".img.tab", torch.cat([tabk, tabv, tabq], 1))
+        F32(d + ".img.tab", _pad_table(torch.cat([tabk, tabv, tabq], 1)))
         lin(d + ".t2i.o", t2i + ".out_proj")
         norm(d + ".n2", s + ".norm2")
         W(d + ".mlp.w1", f[s + ".mlp.lin1.weight"])
@@ -143,8 +152,8 @@ def pack_weights(sd, cfg, device):
     fa = "neck.att.final_attn_token_to_image"
     lin("dmaf.q", fa + ".q_proj")
     W("dmaf.img.w", torch.cat([f[fa + ".k_proj.weight"], f[fa + ".v_proj.weight"]], 0))
-    F32("dmaf.img.tab", torch.cat([kpe @ f[fa + ".k_proj.weight"].t() + f[fa + ".k_proj.bias"],
-                                    f[fa + ".v_proj.bias"].view(1, C // 2).expand(N, C // 2)], 1))
+    F32("dmaf.img.tab", _pad_table(torch.cat([kpe @ f[fa + ".k_proj.weight"].t() + f[fa + ".k_proj.bias"],
+                                               f[fa + ".v_proj.bias"].view(1, C // 2).expand(N, C // 2)], 1)))
     lin("dmaf.o", fa + ".out_proj")
     norm("dmaf.n", "neck.att.norm_final_attn")
 

@@ -72,7 +72,7 @@ def test_module_surface_and_packing_shapes(arch):
         assert packed["pe.w_lo"].shape == (C, 6 * cfg.patch ** 2)
         assert packed["pe.tab"].shape == (N, C)
         assert packed["ffn.w1"].shape == (2048, 904) and not packed["ffn.w1"][:, 899:].any()
-        assert packed["dma0.img.w"].shape == (3 * C // 2, C) and packed["dma0.img.tab"].shape == (N, 3 * C // 2)
+        assert packed["dma0.img.w"].shape == (3 * C // 2, C) and packed["dma0.img.tab"].shape == (N + 128, 3 * C // 2)
         assert packed["d4.a.w"].shape == (4 * cfg.down_4_chan, C)
         assert packed["d32.a.w"].shape == (cfg.down_32_chan, 4 * C)
         assert "hd.seg.b" in scalars

@@ -79,6 +79,38 @@ def test_gemm_epilogues(impl):
     assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K,R", [(784 * 5 + 300, 1152, 768, 784), (1024 * 3, 1280, 1280, 1024), (700, 768, 768, 784)])
+def test_gemm_table_tma_epilogue_matches_generic(M, N, K, R):
+    """Image-side K|V|Q projection (reference transformer.py:444-449): the TMA-staged epilogue (gemm_res.cu MODE_TAB, padded
+    periodic table, ragged last column tile) against fp64 and, bit for bit, against the generic 1-CTA kernel."""
+    from pvpuformer_b200 import ops
+    A, W = _rand_bf16((M, K), 31), _rand_bf16((N, K), 32, 0.05)
+    tab = torch.randn(R, N, device=_dev())
+    padded = torch.cat([tab, tab[:128]], 0).contiguous()
+    out = ops.gemm_table(A, W, padded, R, impl=0)
+    gen = ops.gemm_table(A, W, padded, R, impl=2)
+    idx = torch.arange(M, device=_dev()) % R
+    ref = A.double() @ W.double().t() + tab.double()[idx]
+    assert (out.double() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+    assert torch.equal(out, gen)
+
+
+@pytest.mark.parametrize("M", [50176 // 8, 1000])
+def test_gemm_bf16_residual_2cta_matches_1cta(M):
+    """Image -> tokens out-projection (reference transformer.py:459-461): fp32 out = A W^T + bias + bf16 residual, 2-CTA pairs
+    and 1-CTA kernel bit-identical."""
+    from pvpuformer_b200 import ops
+    N, K = 768, 384
+    A, W = _rand_bf16((M, K), 33), _rand_bf16((N, K), 34, 0.05)
+    bias = torch.randn(N, device=_dev())
+    res = _rand_bf16((M, N), 35)
+    out = ops.gemm(A, W, bias=bias, residual=res, out_dtype=torch.float32, impl=0)
+    gen = ops.gemm(A, W, bias=bias, residual=res, out_dtype=torch.float32, impl=2)
+    ref = A.double() @ W.double().t() + bias.double() + res.double()
+    assert (out.double() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    assert torch.equal(out, gen)
+
+
 @pytest.mark.parametrize("M,K1", [(256, 128), (12544, 1024), (3136 * 3, 256), (50176, 512), (802816 // 8, 128)])
 def test_gemm_b2b_head_pair(M, K1):
     """Back-to-back head GEMM (csrc/gemm_b2b.cu): conv 1x1 + ReLU + fusion-conv slice of one pyramid level with the
