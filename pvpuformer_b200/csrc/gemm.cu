@@ -882,7 +882,7 @@ static int g_stages = 0;
 static int g_cluster = 2;
 static int g_ablate = 0;
 static bool g_ragged256 = true;
-static int g_gn_tma = 1;                // VPU_GEMM_GN_TMA (-DVPU_DEBUG builds): 0 keeps the GroupNorm-fused neck GEMMs on the generic epilogue
+static int g_gn_tma = 3;                // VPU_GEMM_GN_TMA (-DVPU_DEBUG builds): bit 0 GroupNorm-fused neck GEMMs, bit 1 pixel-shuffle GEMMs on gemm_gn.cu
 static int g_res_modes = 1;             // VPU_GEMM_RES_MODES (-DVPU_DEBUG builds): 0 keeps the table GEMMs on the generic epilogue
 static int g_res_kmax = 1 << 30;       // VPU_GEMM_RES_KMAX (-DVPU_DEBUG builds): largest K that takes gemm_res.cu (0 = never)
 static std::mutex g_mu;
@@ -1125,7 +1125,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, int impl) {
         return launch_tc2<256>(p, stream);
     }
     // HBM-bound GroupNorm-fused neck GEMMs (K < 2 N, bf16 output + statistics): TMA-staged epilogue of gemm_gn.cu, same bits
-    if (impl == 0 && g_use_2cta && g_gn_tma && gemm_gn_supported(p)) return gemm_gn_launch(p, stream);
+    if (impl == 0 && g_use_2cta && (g_gn_tma & 1) && gemm_gn_supported(p)) return gemm_gn_launch(p, stream);
+    if (impl == 0 && g_use_2cta && (g_gn_tma & 2) && gemm_ps_tma_supported(p)) return gemm_ps_tma_launch(p, stream);
     // the DMA stage's image-side K|V|Q projections: positional table through the TMA-staged epilogue of gemm_res.cu
     if (impl == 0 && g_use_2cta && g_res_modes && gemm_tab_supported(p)) return gemm_tab_launch(p, stream);
     if (impl == 1) {

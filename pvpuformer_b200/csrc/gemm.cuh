@@ -94,6 +94,9 @@ int gemm_tab_launch(const GemmProblem& p, cudaStream_t stream);
 // GroupNorm-fused neck GEMM with a TMA-staged epilogue (gemm_gn.cu): bf16 out = [rstd (A W^T) - mean rstd wg] + bias, int64 statistics
 bool gemm_gn_supported(const GemmProblem& p);
 int gemm_gn_launch(const GemmProblem& p, cudaStream_t stream);
+// ConvTranspose2d(k=2, s=2) GEMMs of the neck: pixel-shuffle store as one 5-D TMA box per 64-column group (gemm_gn.cu, PS mode)
+bool gemm_ps_tma_supported(const GemmProblem& p);
+int gemm_ps_tma_launch(const GemmProblem& p, cudaStream_t stream);
 
 // Back-to-back GEMM pair of the segmentation head (gemm_b2b.cu): per pyramid level the 1x1 conv + ReLU and that level's
 // [256, 256] slice of the fusion conv (reference swin_transformer.py:723-737; the slice is applied at native resolution

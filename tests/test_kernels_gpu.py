@@ -176,6 +176,22 @@ def test_gemm_pixel_shuffle_matches_conv_transpose(impl):
     assert (out.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,g,cin,cout", [(3, 28, 768, 384), (2, 56, 384, 192), (2, 32, 1280, 640), (1, 64, 640, 320)])
+def test_gemm_pixel_shuffle_tma_store_matches_generic(B, g, cin, cout):
+    """Neck ConvTranspose2d(2, 2) shapes (is_vpu_model.py:57-75; ViT-B g = 28 / 56, ViT-H g = 32 / 64): the 5-D TMA pixel-shuffle
+    store of gemm_gn.cu (whole grid rows per CTA: 112 of 128 accumulator rows at g = 28 / 56) bit for bit against the 1-CTA kernel."""
+    from pvpuformer_b200 import ops
+    x = _rand_bf16((B, g, g, cin), 36)
+    wp = _rand_bf16((4 * cout, cin), 37, 0.05)
+    b4 = torch.randn(cout, device=_dev()).repeat(4).contiguous()
+    out = ops.gemm_pixel_shuffle(x.view(-1, cin), wp, b4, g, cout, impl=0)
+    gen = ops.gemm_pixel_shuffle(x.view(-1, cin), wp, b4, g, cout, impl=2)
+    y = (x.view(-1, cin).double() @ wp.double().t() + b4.double()).view(B, g, g, 2, 2, cout)
+    ref = y.permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * g, 2 * g, cout)
+    assert (out.double() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+    assert torch.equal(out, gen)
+
+
 def _attn_ref(q, k, v, scale):
     a = torch.softmax((q.float() @ k.float().transpose(-1, -2)) * scale, dim=-1)
     return a @ v.float()
