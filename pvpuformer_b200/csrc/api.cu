@@ -129,21 +129,17 @@ Plan make_plan(const vpu_context& h, int B) {
     p.add("Q0", MQ * C * 4);
     p.add("Q0b", MQ * C * 2);
     p.add("Qt", MQ * C * 4);
-    p.add("Qb", MQ * C * 2);
-    p.add("QPb", MQ * C * 2);
+    p.add("QQ", MQ * 2 * C * 2);        // [tokens + PE | tokens] bf16, side by side: the A operand of the merged token projections
     p.add("ql0", MQ * C * 4);
     p.add("ql1", MQ * C * 4);
     p.add("ql2", MQ * C * 4);
     p.add("qfin", MQ * C * 4);
-    p.add("SQK", MQ * 2 * C * 2);
-    p.add("SV", MQ * C * 2);
+    p.add("TOK", MQ * 4 * C * 2);       // merged token projections: i2t K | i2t V | self-attention Q | K | V (or the final q)
     p.add("SO", MQ * C * 2);
     p.add("T", MQ * C * 4);
     p.add("TQ", MQ * (C / 2) * 2);
     p.add("TO", MQ * (C / 2) * 2);
     p.add("MH", MQ * h.d.dma_mlp_dim * 2);
-    p.add("IK", MQ * (C / 2) * 2);
-    p.add("IV", MQ * (C / 2) * 2);
     p.add("X0b", M * C * 2);
     p.add("Kb", M * C * 2);
     p.add("KVQ", M * (3 * C / 2) * 2);
@@ -283,10 +279,10 @@ struct Fwd {
         return grc;
     }
     int ln(const float* in, const std::string& key, float eps, int rows, float* of, __nv_bfloat16* ob,
-           const float* pe = nullptr, __nv_bfloat16* ope = nullptr, float* rowmax = nullptr) {
+           const float* pe = nullptr, __nv_bfloat16* ope = nullptr, float* rowmax = nullptr, int ld_bf16 = 0) {
         LnArgs a;
         a.in = in; a.gamma = Wf(key + ".g"); a.beta = Wf(key + ".b"); a.eps = eps; a.rows = rows;
-        a.out_f32 = of; a.out_bf16 = ob; a.pe = pe; a.out_pe_bf16 = ope; a.rowmax = rowmax;
+        a.out_f32 = of; a.out_bf16 = ob; a.pe = pe; a.out_pe_bf16 = ope; a.rowmax = rowmax; a.ld_bf16 = ld_bf16;
         const double by = (double)rows * h.C() * (4 + (of ? 4 : 0) + (ob ? 2 : 0) + (ope ? 6 : 0));
         return timed("ln", 0, by, [&] { return layernorm_launch(a, h.C(), s); });
     }
@@ -439,8 +435,13 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
 
     // ---- A11-A13: Dual-cross Merging Attention ----
     bf* Q0b = f.buf<bf>("Q0b");
-    bf* Qb = f.buf<bf>("Qb");
-    bf* QPb = f.buf<bf>("QPb");
+    // the two bf16 views of the prompt tokens live side by side, [tokens + PE | tokens] with row stride 2 C: every projection that
+    // reads the same token state runs as ONE GEMM over that pair (block weights [W 0] / [0 W], packing.py), 9 launches fewer
+    bf* QPb = f.buf<bf>("QQ");
+    bf* Qb = QPb + C;
+    const int ldq = 2 * (int)C;
+    bf* TOK = f.buf<bf>("TOK");
+    const int ldt = 4 * (int)C;
     float* Qt = f.buf<float>("Qt");
     float* T = f.buf<float>("T");
     bf* Kb = f.buf<bf>("Kb");
@@ -454,50 +455,50 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     const float* Qf = Q0;  // current fp32 queries
     const bf* Kin = X0b;   // current bf16 keys
     float* ql[3] = {f.buf<float>("ql0"), f.buf<float>("ql1"), f.buf<float>("ql2")};
+    // TOK columns: [0, Ci) i2t K, [Ci, C) i2t V, [C, 3C) self-attention Q | K, [3C, 4C) self-attention V (final layer: [C, C + Ci) = final q)
+    bf* SQK = TOK + C;
+    bf* SV = TOK + 3 * C;
+    // layer 0: no positional term, q, k and v all read the PPuE tokens (transformer.py:436-442)
+    RUN(f.gemm(Q0b, C, "dma0.sa.qkv.w", MQ, 3 * C, C, f.Wf("dma0.sa.qkv.b"), SQK, true, ldt));
     for (int j = 0; j < h.d.dma_depth; ++j) {
         const std::string k = "dma" + std::to_string(j);
-        // (1) prompt self-attention (layer 0: no PE, output replaces the queries; transformer.py:436-442)
-        const bf* qk_in = j == 0 ? Q0b : QPb;
-        const bf* v_in = j == 0 ? Q0b : Qb;
-        RUN(f.gemm(qk_in, C, k + ".sa.qk.w", MQ, 2 * C, C, f.Wf(k + ".sa.qk.b"), f.buf<bf>("SQK"), true, 2 * C));
-        RUN(f.gemm(v_in, C, k + ".sa.v.w", MQ, C, C, f.Wf(k + ".sa.v.b"), f.buf<bf>("SV"), true, C));
-        RUN(f.attn(f.buf<bf>("SQK"), 2 * C, 0, f.buf<bf>("SQK"), 2 * C, C, f.buf<bf>("SV"), C, 0, f.buf<bf>("SO"), C, Q, Q, dh,
-                   dself, B, 1.0f / sqrtf((float)dself), false));
+        const bool last = j + 1 == h.d.dma_depth;
+        // (1) prompt self-attention (layer 0: output replaces the queries)
+        RUN(f.attn(SQK, ldt, 0, SQK, ldt, C, SV, ldt, 0, f.buf<bf>("SO"), C, Q, Q, dh, dself, B, 1.0f / sqrtf((float)dself), false));
         RUN(f.gemm(f.buf<bf>("SO"), C, k + ".sa.o.w", MQ, C, C, f.Wf(k + ".sa.o.b"), T, false, C, ACT_NONE,
                    j == 0 ? nullptr : Qf, false, C));
-        RUN(f.ln(T, k + ".n1", 1e-5f, MQ, Qt, Qb, Q0, QPb));
+        RUN(f.ln(T, k + ".n1", 1e-5f, MQ, Qt, Qb, Q0, QPb, nullptr, ldq));
         Qf = Qt;
         // (2) tokens -> image cross attention; the image-side K|V (and step 4's Q) come from one GEMM whose
         //     positional term key_pe W^T is a precomputed additive table (transformer.py:444-449)
-        RUN(f.gemm(QPb, C, k + ".t2i.q.w", MQ, Ci, C, f.Wf(k + ".t2i.q.b"), f.buf<bf>("TQ"), true, Ci));
+        RUN(f.gemm(QPb, ldq, k + ".t2i.q.w", MQ, Ci, C, f.Wf(k + ".t2i.q.b"), f.buf<bf>("TQ"), true, Ci));
         RUN(f.gemm(Kin, C, k + ".img.w", M, 3 * Ci, C, nullptr, KVQ, true, 3 * Ci, ACT_NONE, nullptr, false, 0,
                    f.Wf(k + ".img.tab"), N, nullptr, nullptr, TAB_PAD));
         RUN(f.attn(f.buf<bf>("TQ"), Ci, 0, KVQ, 3 * Ci, 0, KVQ, 3 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
                    1.0f / sqrtf((float)dcross), false));
         RUN(f.gemm(f.buf<bf>("TO"), Ci, k + ".t2i.o.w", MQ, C, Ci, f.Wf(k + ".t2i.o.b"), T, false, C, ACT_NONE, Qf, false, C));
-        RUN(f.ln(T, k + ".n2", 1e-5f, MQ, Qt, Qb, Q0, QPb));
+        RUN(f.ln(T, k + ".n2", 1e-5f, MQ, Qt, Qb, Q0, QPb, nullptr, ldq));
         // (3) MLP (transformer.py:451-454)
-        RUN(f.gemm(Qb, C, k + ".mlp.w1", MQ, h.d.dma_mlp_dim, C, f.Wf(k + ".mlp.b1"), f.buf<bf>("MH"), true, h.d.dma_mlp_dim,
+        RUN(f.gemm(Qb, ldq, k + ".mlp.w1", MQ, h.d.dma_mlp_dim, C, f.Wf(k + ".mlp.b1"), f.buf<bf>("MH"), true, h.d.dma_mlp_dim,
                    ACT_RELU));
         RUN(f.gemm(f.buf<bf>("MH"), h.d.dma_mlp_dim, k + ".mlp.w2", MQ, C, h.d.dma_mlp_dim, f.Wf(k + ".mlp.b2"), T, false, C,
                    ACT_NONE, Qf, false, C));
-        RUN(f.ln(T, k + ".n3", 1e-5f, MQ, ql[j], Qb, Q0, QPb));
+        RUN(f.ln(T, k + ".n3", 1e-5f, MQ, ql[j], Qb, Q0, QPb, nullptr, ldq));
         Qf = ql[j];
-        // (4) image -> tokens cross attention (transformer.py:456-461)
-        RUN(f.gemm(QPb, C, k + ".i2t.k.w", MQ, Ci, C, f.Wf(k + ".i2t.k.b"), f.buf<bf>("IK"), true, Ci));
-        RUN(f.gemm(Qb, C, k + ".i2t.v.w", MQ, Ci, C, f.Wf(k + ".i2t.v.b"), f.buf<bf>("IV"), true, Ci));
-        RUN(f.attn(KVQ, 3 * Ci, 2 * Ci, f.buf<bf>("IK"), Ci, 0, f.buf<bf>("IV"), Ci, 0, f.buf<bf>("IO"), Ci, N, Q, dh, dcross, B,
+        // (4) image -> tokens cross attention (transformer.py:456-461).  Its K (tokens + PE) and V (tokens) projections, the next
+        //     layer's self-attention q | k (tokens + PE) and v (tokens) -- or the final attention's q -- all read this token state
+        RUN(f.gemm(QPb, ldq, k + ".tok.w", MQ, last ? 3 * Ci : 4 * C, 2 * C, f.Wf(k + ".tok.b"), TOK, true, ldt));
+        RUN(f.attn(KVQ, 3 * Ci, 2 * Ci, TOK, ldt, 0, TOK, ldt, Ci, f.buf<bf>("IO"), Ci, N, Q, dh, dcross, B,
                    1.0f / sqrtf((float)dcross), false));
         RUN(f.gemm(f.buf<bf>("IO"), Ci, k + ".i2t.o.w", M, C, Ci, f.Wf(k + ".i2t.o.b"), f.buf<float>("T2"), false, C, ACT_NONE,
                    Kin, true, C));
         RUN(f.ln(f.buf<float>("T2"), k + ".n4", 1e-5f, M, nullptr, Kb, nullptr, nullptr, rowmax + (size_t)j * M));
         Kin = Kb;
     }
-    // final tokens -> image attention (transformer.py:374-379)
-    RUN(f.gemm(QPb, C, "dmaf.q.w", MQ, Ci, C, f.Wf("dmaf.q.b"), f.buf<bf>("TQ"), true, Ci));
+    // final tokens -> image attention (transformer.py:374-379); its q sits in TOK[:, C : C + Ci)
     RUN(f.gemm(Kin, C, "dmaf.img.w", M, 2 * Ci, C, nullptr, KVQ, true, 2 * Ci, ACT_NONE, nullptr, false, 0,
                f.Wf("dmaf.img.tab"), N, nullptr, nullptr, TAB_PAD));
-    RUN(f.attn(f.buf<bf>("TQ"), Ci, 0, KVQ, 2 * Ci, 0, KVQ, 2 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
+    RUN(f.attn(TOK, ldt, C, KVQ, 2 * Ci, 0, KVQ, 2 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
                1.0f / sqrtf((float)dcross), false));
     RUN(f.gemm(f.buf<bf>("TO"), Ci, "dmaf.o.w", MQ, C, Ci, f.Wf("dmaf.o.b"), T, false, C, ACT_NONE, Qf, false, C));
     RUN(f.ln(T, "dmaf.n", 1e-5f, MQ, f.buf<float>("qfin"), nullptr));
@@ -665,15 +666,15 @@ std::vector<Need> needed_weights(const vpu_context& h) {
     lin2("ffn", "2", C, h.d.ppue_ffn_dim);
     for (int j = 0; j < h.d.dma_depth; ++j) {
         const std::string k = "dma" + std::to_string(j);
-        lin(k + ".sa.qk", 2 * C, C); lin(k + ".sa.v", C, C); lin(k + ".sa.o", C, C); nrm(k + ".n1", C);
+        if (j == 0) lin(k + ".sa.qkv", 3 * C, C);
+        lin(k + ".sa.o", C, C); nrm(k + ".n1", C);
         lin(k + ".t2i.q", Ci, C);
         v.push_back({k + ".img.w", VPU_BF16, {3 * Ci, C}});
         v.push_back({k + ".img.tab", VPU_F32, {N + TAB_PAD, 3 * Ci}});   // rows 0 .. TAB_PAD-1 repeated at the end
         lin(k + ".t2i.o", C, Ci); nrm(k + ".n2", C);
         lin2(k + ".mlp", "1", h.d.dma_mlp_dim, C); lin2(k + ".mlp", "2", C, h.d.dma_mlp_dim); nrm(k + ".n3", C);
-        lin(k + ".i2t.k", Ci, C); lin(k + ".i2t.v", Ci, C); lin(k + ".i2t.o", C, Ci); nrm(k + ".n4", C);
+        lin(k + ".tok", j + 1 == h.d.dma_depth ? 3 * Ci : 4 * C, 2 * C);   // merged token projections (packing.py) lin(k + ".i2t.o", C, Ci); nrm(k + ".n4", C);
     }
-    lin("dmaf.q", Ci, C);
     v.push_back({"dmaf.img.w", VPU_BF16, {2 * Ci, C}});
     v.push_back({"dmaf.img.tab", VPU_F32, {N + TAB_PAD, 2 * Ci}});
     lin("dmaf.o", C, Ci); nrm("dmaf.n", C);

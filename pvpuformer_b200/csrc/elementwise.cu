@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
     }
     const float rstd = rsqrtf(warp_sum(var) * (1.0f / C) + a.eps);
     float mx = -INFINITY;
+    const int ldb = a.ld_bf16 ? a.ld_bf16 : C;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         const int c4 = lane + 32 * i;
@@ -48,12 +49,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
         if (a.out_f32) reinterpret_cast<float4*>(a.out_f32 + (size_t)row * C)[c4] = y;
         if (a.out_bf16) {
             uint2 o = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
-            reinterpret_cast<uint2*>(a.out_bf16 + (size_t)row * C)[c4] = o;
+            reinterpret_cast<uint2*>(a.out_bf16 + (size_t)row * ldb)[c4] = o;
         }
         if (a.out_pe_bf16) {
             const float4 p = reinterpret_cast<const float4*>(a.pe + (size_t)row * C)[c4];
             uint2 o = make_uint2(pack_bf16(y.x + p.x, y.y + p.y), pack_bf16(y.z + p.z, y.w + p.w));
-            reinterpret_cast<uint2*>(a.out_pe_bf16 + (size_t)row * C)[c4] = o;
+            reinterpret_cast<uint2*>(a.out_pe_bf16 + (size_t)row * ldb)[c4] = o;
         }
     }
     if (a.rowmax) {

@@ -15,6 +15,7 @@ struct LnArgs {
     __nv_bfloat16* out_pe_bf16 = nullptr;  // optional: bf16(y + pe[row])
     const float* pe = nullptr;
     float* rowmax = nullptr;            // optional: max_c y
+    int ld_bf16 = 0;                    // row stride of the two bf16 outputs (elements); 0 = C
 };
 int layernorm_launch(const LnArgs& a, int C, cudaStream_t stream);
 

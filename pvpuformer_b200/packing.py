@@ -125,9 +125,9 @@ def pack_weights(sd, cfg, device):
     for j in range(cfg.dma_depth):
         s, d = "neck.att.layers.%d" % j, "dma%d" % j
         sa = s + ".self_attn"
-        W(d + ".sa.qk.w", torch.cat([f[sa + ".q_proj.weight"], f[sa + ".k_proj.weight"]], 0))
-        F32(d + ".sa.qk.b", torch.cat([f[sa + ".q_proj.bias"], f[sa + ".k_proj.bias"]], 0))
-        lin(d + ".sa.v", sa + ".v_proj")
+        if j == 0:      # layer 0: q, k and v all read the PPuE tokens (no positional term): one [3C, C] projection
+            W(d + ".sa.qkv.w", torch.cat([f[sa + ".q_proj.weight"], f[sa + ".k_proj.weight"], f[sa + ".v_proj.weight"]], 0))
+            F32(d + ".sa.qkv.b", torch.cat([f[sa + ".q_proj.bias"], f[sa + ".k_proj.bias"], f[sa + ".v_proj.bias"]], 0))
         lin(d + ".sa.o", sa + ".out_proj")
         norm(d + ".n1", s + ".norm1")
         t2i, i2t = s + ".cross_attn_token_to_image", s + ".cross_attn_image_to_token"
@@ -145,12 +145,28 @@ def pack_weights(sd, cfg, device):
         W(d + ".mlp.w2", f[s + ".mlp.lin2.weight"])
         F32(d + ".mlp.b2", f[s + ".mlp.lin2.bias"])
         norm(d + ".n3", s + ".norm3")
-        lin(d + ".i2t.k", i2t + ".k_proj")
-        lin(d + ".i2t.v", i2t + ".v_proj")
+        # every projection that reads the token state after norm3 as ONE GEMM over A = [tokens + PE | tokens] (K = 2C):
+        # image->token k (tokens + PE) and v (tokens) of this layer, then the next layer's self-attention q | k (tokens + PE) and
+        # v (tokens), or after the last layer the final attention's q (tokens + PE).  Block rows [W 0] / [0 W].
+        blocks = [(f[i2t + ".k_proj.weight"], 0), (f[i2t + ".v_proj.weight"], 1)]       # (weight, 0 = reads tokens + PE / 1 = reads tokens)
+        bias = [f[i2t + ".k_proj.bias"], f[i2t + ".v_proj.bias"]]
+        if j + 1 < cfg.dma_depth:
+            nsa = "neck.att.layers.%d.self_attn" % (j + 1)
+            blocks += [(f[nsa + ".q_proj.weight"], 0), (f[nsa + ".k_proj.weight"], 0), (f[nsa + ".v_proj.weight"], 1)]
+            bias += [f[nsa + ".q_proj.bias"], f[nsa + ".k_proj.bias"], f[nsa + ".v_proj.bias"]]
+        else:
+            fq = "neck.att.final_attn_token_to_image.q_proj"
+            blocks += [(f[fq + ".weight"], 0)]
+            bias += [f[fq + ".bias"]]
+        rows = []
+        for wblk, side in blocks:
+            z = torch.zeros_like(wblk)
+            rows.append(torch.cat([wblk, z], 1) if side == 0 else torch.cat([z, wblk], 1))
+        W(d + ".tok.w", torch.cat(rows, 0))
+        F32(d + ".tok.b", torch.cat(bias, 0))
         lin(d + ".i2t.o", i2t + ".out_proj")
         norm(d + ".n4", s + ".norm4")
     fa = "neck.att.final_attn_token_to_image"
-    lin("dmaf.q", fa + ".q_proj")
     W("dmaf.img.w", torch.cat([f[fa + ".k_proj.weight"], f[fa + ".v_proj.weight"]], 0))
     F32("dmaf.img.tab", _pad_table(torch.cat([kpe @ f[fa + ".k_proj.weight"].t() + f[fa + ".k_proj.bias"],
                                                f[fa + ".v_proj.bias"].view(1, C // 2).expand(N, C // 2)], 1)))
