@@ -127,6 +127,12 @@ int vpu_gemm_b2b(const void* A_bf16, int lda, const void* W1_bf16, const float* 
  * last one.  out[M,N] (bf16) = A[M,K] * W[N,K]^T + table[m % table_rows, N] */
 int vpu_gemm_table(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* table, int table_rows,
                    int table_pad_rows, void* out_bf16, int ldo, int impl, void* stream);
+/* image -> tokens out-projection + residual + norm4 of a Dual-cross Merging Attention layer (reference transformer.py:459-463) in one
+ * kernel: out[M,C] (bf16) = LayerNorm_C(A[M,K] * W[C,K]^T + bias + res[M,C]) * gamma + beta; C = 512 ... 1280, a multiple of 256.
+ * rowmax_parts (may be NULL): fp32 [C / 256, M], the maximum of row m over each 256-column block of out (before bf16 rounding) */
+int vpu_gemm_layernorm(const void* A_bf16, int lda, const void* W_bf16, int ldw, const float* bias, const void* res_bf16, int ldr,
+                       const float* gamma, const float* beta, float eps, int M, int K, int C, void* out_bf16, int ldo,
+                       float* rowmax_parts, void* stream);
 /* ConvTranspose2d(k=2,s=2) as GEMM + pixel-shuffle store: A [B*g*g, K] -> out NHWC [B, 2g, 2g, cout] bf16 */
 int vpu_gemm_pixel_shuffle(const void* A_bf16, const void* W_bf16, int M, int cout, int K, const float* bias4, int g,
                            void* out_bf16, int impl, void* stream);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvpuformer_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["gemm.cu", "gemm_b2b.cu", "gemm_res.cu", "gemm_gn.cu", "head_tail.cu", "attention.cu", "attention_tc.cu", "attention_dma.cu", "prompt.cu", "elementwise.cu", "noc.cu", "session.cu", "raster.cu", "api.cu"]
+SOURCES = ["gemm.cu", "gemm_b2b.cu", "gemm_res.cu", "gemm_gn.cu", "gemm_ln.cu", "head_tail.cu", "attention.cu", "attention_tc.cu", "attention_dma.cu", "prompt.cu", "elementwise.cu", "noc.cu", "session.cu", "raster.cu", "api.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

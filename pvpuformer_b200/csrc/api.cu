@@ -145,7 +145,7 @@ Plan make_plan(const vpu_context& h, int B) {
     p.add("KVQ", M * (3 * C / 2) * 2);
     p.add("IO", M * (C / 2) * 2);
     p.add("T2", M * C * 4);
-    p.add("rowmax", 3 * M * 4);
+    p.add("rowmax", 3 * (size_t)gemm_ln_parts((int)C) * M * 4);   // [layer][column block][token]: partial row maxima (gemm_ln.cu)
     p.add("qout", MQ * C * 4);
     p.add("qout_b", MQ * C * 2);
     p.add("cg", 3 * (size_t)B * C * 4);
@@ -455,6 +455,8 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     const float* Qf = Q0;  // current fp32 queries
     const bf* Kin = X0b;   // current bf16 keys
     float* ql[3] = {f.buf<float>("ql0"), f.buf<float>("ql1"), f.buf<float>("ql2")};
+    static const bool use_gemm_ln = [] { const char* e = vpu_debug_env("VPU_DMA_GEMM_LN"); return !(e && e[0] == '0'); }();   // A/B knob, -DVPU_DEBUG builds
+    const int rm_parts = gemm_ln_parts((int)C);
     // TOK columns: [0, Ci) i2t K, [Ci, C) i2t V, [C, 3C) self-attention Q | K, [3C, 4C) self-attention V (final layer: [C, C + Ci) = final q)
     bf* SQK = TOK + C;
     bf* SV = TOK + 3 * C;
@@ -490,9 +492,26 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         RUN(f.gemm(QPb, ldq, k + ".tok.w", MQ, last ? 3 * Ci : 4 * C, 2 * C, f.Wf(k + ".tok.b"), TOK, true, ldt));
         RUN(f.attn(KVQ, 3 * Ci, 2 * Ci, TOK, ldt, 0, TOK, ldt, Ci, f.buf<bf>("IO"), Ci, N, Q, dh, dcross, B,
                    1.0f / sqrtf((float)dcross), false));
-        RUN(f.gemm(f.buf<bf>("IO"), Ci, k + ".i2t.o.w", M, C, Ci, f.Wf(k + ".i2t.o.b"), f.buf<float>("T2"), false, C, ACT_NONE,
-                   Kin, true, C));
-        RUN(f.ln(f.buf<float>("T2"), k + ".n4", 1e-5f, M, nullptr, Kb, nullptr, nullptr, rowmax + (size_t)j * M));
+        //     out-projection + residual + norm4 in one kernel (gemm_ln.cu); the row maxima the merge gates need come out as one
+        //     partial per 256-column block
+        GemmLn gl;
+        gl.A = f.buf<bf>("IO"); gl.lda = Ci; gl.W = f.Wb(k + ".i2t.o.w"); gl.ldw = Ci; gl.bias = f.Wf(k + ".i2t.o.b");
+        gl.res = Kin; gl.ldr = C; gl.gamma = f.Wf(k + ".n4.g"); gl.beta = f.Wf(k + ".n4.b"); gl.out = Kb; gl.ldo = C;
+        gl.rowmax_parts = rowmax + (size_t)j * rm_parts * M; gl.M = M; gl.K = Ci; gl.C = C;
+        if (use_gemm_ln && gemm_ln_supported(gl)) {
+            f.label = k + ".i2t.o+n4 " + std::to_string(M) + "x" + std::to_string(C) + "x" + std::to_string(Ci);
+            const int grc = f.timed("gemm_ln", 2.0 * M * C * Ci, (double)M * (2.0 * Ci + 4.0 * C) + 2.0 * C * Ci,
+                                    [&] { return gemm_ln_launch(gl, s); });
+            f.label.clear();
+            if (grc) return grc;
+        } else {
+            RUN(f.gemm(f.buf<bf>("IO"), Ci, k + ".i2t.o.w", M, C, Ci, f.Wf(k + ".i2t.o.b"), f.buf<float>("T2"), false, C, ACT_NONE,
+                       Kin, true, C));
+            RUN(f.ln(f.buf<float>("T2"), k + ".n4", 1e-5f, M, nullptr, Kb, nullptr, nullptr, rowmax + (size_t)j * rm_parts * M));
+            for (int q = 1; q < rm_parts; ++q)      // the other partial maxima: copies of the full-row maximum
+                VPU_CHECK_CUDA(cudaMemcpyAsync(rowmax + ((size_t)j * rm_parts + q) * M, rowmax + (size_t)j * rm_parts * M, (size_t)M * 4,
+                                               cudaMemcpyDeviceToDevice, s));
+        }
         Kin = Kb;
     }
     // final tokens -> image attention (transformer.py:374-379); its q sits in TOK[:, C : C + Ci)
@@ -510,7 +529,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
                                 f.buf<float>("cg"), s);
     }));
     MergeArgs ma;
-    ma.x = X; ma.cg = f.buf<float>("cg"); ma.rowmax = rowmax; ma.x2 = f.buf<bf>("x2"); ma.x3 = f.buf<bf>("x3");
+    ma.x = X; ma.cg = f.buf<float>("cg"); ma.rowmax = rowmax; ma.rowmax_parts = rm_parts; ma.x2 = f.buf<bf>("x2"); ma.x3 = f.buf<bf>("x3");
     ma.x4_s2d = f.buf<bf>("x4"); ma.B = B; ma.N = N; ma.M = M; ma.C = C; ma.grid = g;
     RUN(f.timed("merge", 0, 10.0 * M * C, [&] { return merge_launch(ma, s); }));
 
@@ -901,6 +920,17 @@ int vpu_gemm_table(const void* A, int lda, const void* W, int ldw, int M, int N,
     p.epi.out = out; p.epi.out_bf16 = 1; p.epi.ldo = ldo; p.epi.bias2d = table; p.epi.bias2d_rows = table_rows;
     p.epi.bias2d_pad_rows = table_pad_rows;
     return gemm_launch(p, reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int vpu_gemm_layernorm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* res, int ldr, const float* gamma,
+                       const float* beta, float eps, int M, int K, int C, void* out, int ldo, float* rowmax_parts, void* stream) {
+    VPU_REQUIRE(A && W && bias && res && gamma && beta && out, "vpu_gemm_layernorm: null argument");
+    GemmLn p;
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A); p.W = reinterpret_cast<const __nv_bfloat16*>(W); p.bias = bias;
+    p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out); p.rowmax_parts = rowmax_parts;
+    p.M = M; p.K = K; p.C = C; p.lda = lda; p.ldw = ldw; p.ldr = ldr; p.ldo = ldo;
+    return gemm_ln_launch(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vpu_gemm_b2b(const void* A, int lda, const void* W1, const float* bias1, const void* W2, int M, int K1, void* out, int ldo,

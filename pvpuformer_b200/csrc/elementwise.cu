@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(320) merge_kernel(const MergeArgs a) {
         if (threadIdx.x < 3 * MERGE_ROWS) {
             const int r = threadIdx.x / 3, l = threadIdx.x % 3, m = m0 + r;
             if (m < a.M) {
-                sg_s[r][l] = 1.0f / (1.0f + expf(-a.rowmax[(size_t)l * a.M + m]));
+                float mx = a.rowmax[(size_t)l * a.rowmax_parts * a.M + m];
+                for (int q = 1; q < a.rowmax_parts; ++q) mx = fmaxf(mx, a.rowmax[((size_t)l * a.rowmax_parts + q) * a.M + m]);
+                sg_s[r][l] = 1.0f / (1.0f + expf(-mx));
                 if (l == 0) {
                     const int b = m / a.N, tok = m % a.N, i = tok / g, j = tok % g;
                     b_s[r] = b;

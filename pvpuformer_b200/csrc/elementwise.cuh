@@ -34,7 +34,8 @@ int qout_gate_launch(const float* q0, const float* q1, const float* q2, const fl
 struct MergeArgs {
     const float* x = nullptr;        // backbone tokens fp32 [M, C]
     const float* cg = nullptr;       // [3, B, C] channel gates (already sigmoid)
-    const float* rowmax = nullptr;   // [3, M] per-token max of keys_l (pre-sigmoid)
+    const float* rowmax = nullptr;   // [3, rowmax_parts, M] per-token max of keys_l (pre-sigmoid), as partial maxima over column blocks
+    int rowmax_parts = 1;
     __nv_bfloat16* x0 = nullptr;     // bf16(x)            [M, C]
     __nv_bfloat16* x2 = nullptr;     // merged level 1     [M, C]
     __nv_bfloat16* x3 = nullptr;     // merged level 2     [M, C]

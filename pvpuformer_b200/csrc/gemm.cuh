@@ -91,6 +91,23 @@ int gemm_res_launch(const GemmProblem& p, cudaStream_t stream);
 // same skeleton: bf16 out = A W^T + periodic fp32 table (needs Epi::bias2d_pad_rows >= 128)
 bool gemm_tab_supported(const GemmProblem& p);
 int gemm_tab_launch(const GemmProblem& p, cudaStream_t stream);
+// Out-projection + bf16 residual + LayerNorm in one kernel, a cluster of C / 256 CTAs per 128-row tile (gemm_ln.cu):
+// out (bf16) = LayerNorm_C(A W^T + bias + res) gamma + beta; rowmax_parts[r][m] = max over CTA r's 256 columns of row m (optional)
+struct GemmLn {
+    const __nv_bfloat16* A = nullptr;
+    const __nv_bfloat16* W = nullptr;       // [C, K]
+    const float* bias = nullptr;
+    const __nv_bfloat16* res = nullptr;     // [M, C]
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    __nv_bfloat16* out = nullptr;           // [M, C]
+    float* rowmax_parts = nullptr;          // [gemm_ln_parts(C), M]
+    float eps = 1e-5f;
+    int M = 0, K = 0, C = 0, lda = 0, ldw = 0, ldr = 0, ldo = 0;
+};
+int gemm_ln_parts(int C);
+bool gemm_ln_supported(const GemmLn& p);
+int gemm_ln_launch(const GemmLn& p, cudaStream_t stream);
 // GroupNorm-fused neck GEMM with a TMA-staged epilogue (gemm_gn.cu): bf16 out = [rstd (A W^T) - mean rstd wg] + bias, int64 statistics
 bool gemm_gn_supported(const GemmProblem& p);
 int gemm_gn_launch(const GemmProblem& p, cudaStream_t stream);

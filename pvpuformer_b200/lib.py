@@ -62,6 +62,8 @@ SIGNATURES = {
                               c_void_p, c_void_p]),
     "vpu_gemm_b2b": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "vpu_gemm_table": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vpu_gemm_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
+                                   c_void_p, c_int, c_void_p, c_void_p]),
     "vpu_gemm_pixel_shuffle": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "vpu_attention": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),

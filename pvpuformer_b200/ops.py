@@ -37,6 +37,19 @@ def gemm_table(A, W, table, table_rows, impl=0):
     return out
 
 
+def gemm_layernorm(A, W, bias, res, gamma, beta, eps=1e-5, want_rowmax=True, out=None):
+    """bf16(LayerNorm(A @ W.T + bias + res) * gamma + beta) and the per-256-column-block row maxima [C // 256, M]."""
+    M, K = A.shape
+    C = W.shape[0]
+    if out is None:
+        out = torch.empty(M, C, dtype=torch.bfloat16, device=A.device)
+    parts = torch.empty(C // 256, M, dtype=torch.float32, device=A.device) if want_rowmax else None
+    L.check(L.load().vpu_gemm_layernorm(L.ptr(A), A.stride(0), L.ptr(W), W.stride(0), L.ptr(bias), L.ptr(res), res.stride(0),
+                                        L.ptr(gamma), L.ptr(beta), eps, M, K, C, L.ptr(out), out.stride(0), L.ptr(parts),
+                                        L.current_stream()))
+    return out, parts
+
+
 def gemm_b2b(A, W1, bias1, W2):
     """bf16( bf16(relu(A @ W1.T + bias1)) @ W2.T ): the head's conv + ReLU + fusion-conv slice of one pyramid level."""
     M, K1 = A.shape

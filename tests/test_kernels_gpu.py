@@ -111,6 +111,27 @@ def test_gemm_bf16_residual_2cta_matches_1cta(M):
     assert torch.equal(out, gen)
 
 
+@pytest.mark.parametrize("M,C,K", [(784 * 3, 768, 384), (1024 * 2 + 77, 1280, 640), (50176, 768, 384), (900, 1024, 512)])
+def test_gemm_layernorm_cluster_matches_torch(M, C, K):
+    """Image -> tokens out-projection + residual + norm4 (reference transformer.py:459-463) as one kernel whose CTAs exchange the
+    row moments through distributed shared memory (csrc/gemm_ln.cu): against the same chain in torch fp32, in place over the
+    residual like the forward uses it, and run to run."""
+    from pvpuformer_b200 import ops
+    A, W = _rand_bf16((M, K), 51), _rand_bf16((C, K), 52, K ** -0.5)
+    g = torch.Generator().manual_seed(53)
+    bias, gamma, beta = (torch.randn(C, generator=g).to(_dev()) for _ in range(3))
+    res = _rand_bf16((M, C), 54, 2.0)
+    out, parts = ops.gemm_layernorm(A, W, bias, res, gamma, beta)
+    x = A.float() @ W.float().t() + bias + res.float()
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert (parts.max(0).values - ref.max(1).values).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    inplace = res.clone()
+    out2, parts2 = ops.gemm_layernorm(A, W, bias, inplace, gamma, beta, out=inplace)
+    assert torch.equal(out2, out) and torch.equal(parts2, parts)
+
+
 @pytest.mark.parametrize("M,K1", [(256, 128), (12544, 1024), (3136 * 3, 256), (50176, 512), (802816 // 8, 128)])
 def test_gemm_b2b_head_pair(M, K1):
     """Back-to-back head GEMM (csrc/gemm_b2b.cu): conv 1x1 + ReLU + fusion-conv slice of one pyramid level with the
