@@ -9,7 +9,13 @@
 // (= rows) add bias + residual, write x back into the same TMEM columns and send the row's partial (sum, sum of squares) to every CTA
 // of the cluster with st.async (DSMEM write that completes transaction bytes on the receiver's mbarrier: no cluster-wide barrier, no
 // fences).  Every CTA then adds the NC partials in rank order (same bits everywhere), normalises its columns out of TMEM and stages
-// bf16 rows for a TMA tensor store.  The residual tile arrives by TMA in the same staging tiles the result leaves from.
+// bf16 rows for a TMA tensor store.
+// The residual goes through the tensor core: its [128 x 64] bf16 chunks travel through the operand ring like A chunks and are
+// multiplied by a 16 x 16 identity into the accumulator columns they belong to (16 tcgen05.mma of N = 16 per tile; bf16 x 1.0 is
+// exact in the fp32 accumulator).  The producer warp therefore prefetches the residual with the operands, and the epilogue reads
+// nothing but TMEM; staging it in the output tiles exposed an HBM round trip per tile (84 us against 64 us for ViT-B, batch 64;
+// the unfused pair took 114 us).  What bounds it now (ncu, profiles/ncu_full_r2.md): the 3-stage operand ring -- a 1-CTA tile re-reads
+// its 192 KB weight slice per 128 rows, 352 KB of TMA loads per tile with 144 KB in flight; shared memory is full.
 // Two accumulators: the MMAs of the next row tile run under the epilogue of the current one.
 #include "gemm.cuh"
 #include "tc_attn.cuh"
@@ -23,7 +29,9 @@ constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2, STAGE = A_BYTES + W_
 constexpr int STAGES = 3;
 constexpr int TILE16 = BM * 64 * 2;             // staging tile: [128 rows x 64 bf16], 128-byte swizzle
 constexpr int STG_OFF = STAGES * STAGE;
-constexpr int SMEM = STG_OFF + 4 * TILE16 + 1024;
+constexpr int ID_OFF = STG_OFF + 4 * TILE16;     // 16 x 64 bf16 tile, 128-byte swizzle: row n holds ones at k = n, n + 16, n + 32, n + 48
+constexpr int ID_BYTES = 16 * 128;
+constexpr int SMEM = ID_OFF + ID_BYTES + 1024;
 constexpr int EPI_WARPS = 8;
 constexpr int STORE_WARP = 2 + EPI_WARPS;
 constexpr int THREADS = (STORE_WARP + 1) * 32;
@@ -74,7 +82,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmO, const LnFuseArgs a) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], res_full, stg_full, xbar[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], stg_full, stg_free, xbar[2];
     __shared__ __align__(16) float bias_s[BN], gamma_s[BN], beta_s[BN];
     __shared__ float2 loc_s[2][BM];                  // the two column halves' partials of a row, combined before they are sent
     __shared__ __align__(8) float2 part_s[2][NC][BM];   // [exchange buffer][source CTA][row]: written by the peers (st.async)
@@ -86,6 +94,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int rank = (int)cluster_ctarank();
     constexpr uint32_t XBYTES = NC * BM * 8;         // bytes one exchange delivers to a CTA
 
+    // identity operand of the residual MMAs: element (n, k) = 1 iff k mod 16 == n, in the swizzled K-major layout (16-byte chunk c of
+    // row n sits at chunk c ^ (n & 7))
+    for (int i = threadIdx.x; i < 16 * 8; i += THREADS) {
+        const int n = i >> 3, c = i & 7;             // chunk c = k in [8c, 8c + 8)
+        uint32_t w[4] = {0, 0, 0, 0};
+        const int kk = n - (c & 1) * 8;              // position of the one inside this chunk, if any
+        if (kk >= 0 && kk < 8) w[kk >> 1] = (kk & 1) ? 0x3F800000u : 0x00003F80u;
+        *reinterpret_cast<uint4*>(smem + ID_OFF + n * 128 + ((c ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO);
         for (int s = 0; s < STAGES; ++s) {
@@ -97,8 +115,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&acc_empty[i], EPI_WARPS);
             mbar_init(&xbar[i], 1);
         }
-        mbar_init(&res_full, 1);
         mbar_init(&stg_full, EPI_WARPS);
+        mbar_init(&stg_free, 1);
         fence_barrier_init();
         // armed before any peer can send (the cluster barrier below): exchanges 0 and 1
         mbar_arrive_expect_tx(&xbar[0], XBYTES);
@@ -135,11 +153,22 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            for (int j = 0; j < BN / 128; ++j) {     // the residual's four 64-column chunks, two per stage (A slot + head of the W slot)
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_bar[stage], 2 * A_BYTES);
+                    tma_load_2d(smem + stage * STAGE, &tmR, &full_bar[stage], col0 + j * 128, t * BM);
+                    tma_load_2d(smem + stage * STAGE + A_BYTES, &tmR, &full_bar[stage], col0 + j * 128 + 64, t * BM);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN), idesc_r = umma_idesc_bf16(BM, 16);
         const uint64_t adesc0 = umma_desc_k_sw128(smem_base), bdesc0 = umma_desc_k_sw128(smem_base + A_BYTES);
+        const uint64_t idesc0 = umma_desc_k_sw128(smem_base + ID_OFF);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         for (int t = cl; t < row_tiles; t += ncl) {
@@ -154,7 +183,22 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, adesc0 + soff + 2 * k, bdesc0 + soff + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);
-                    if (kb + 1 == kblks) umma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            for (int j = 0; j < BN / 128; ++j) {     // + residual: 64-column chunk times the identity into columns [64 chunk + 16 k, + 16)
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t soff = (uint64_t)(stage * (STAGE >> 4));
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(d_tmem + (2 * j + h) * 64 + k * 16, adesc0 + soff + (uint64_t)(h * (A_BYTES >> 4)) + 2 * k, idesc0 + 2 * k, idesc_r, 1u);
+                    umma_commit(&empty_bar[stage]);
+                    if (j + 1 == BN / 128) umma_commit(&acc_full[acc]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -181,33 +225,33 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m = t * BM + row;
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            mbar_wait(&res_full, tile_phase);        // the residual tile of these rows has landed in the staging tiles
             const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
-            // pass 1: x = (acc + bias) + residual, back into TMEM; the row's partial moments over this warp's 128 columns
+            // pass 1: x = accumulator (A W^T + residual) + bias; the row's partial moments over this warp's 128 columns.  The TMEM
+            // load of chunk c + 1 is in flight while chunk c is reduced
             float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_acc + c * 32, r);
-                const uint8_t* rrow = smem + STG_OFF + (half * 2 + (c >> 1)) * TILE16 + row * 128;
-                const float* bb = bias_s + half * 128 + c * 32;
-                tmem_ld_wait();
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32(t_acc, ra);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint4 rv = *reinterpret_cast<const uint4*>(rrow + ((((c & 1) * 4 + u) ^ sw) << 4));
-                    const float2 r0 = unpack_bf16(rv.x), r1 = unpack_bf16(rv.y), r2 = unpack_bf16(rv.z), r3 = unpack_bf16(rv.w);
-                    const float rs[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+                for (int c = 0; c < 4; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x32(t_acc + (c + 1) * 32, rb);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float x = (__uint_as_float(r[8 * u + e]) + bb[8 * u + e]) + rs[e];
+                    for (int e = 0; e < 32; ++e) {
+                        const float x = __uint_as_float(ra[e]) + bias_s[half * 128 + c * 32 + e];
                         s1 += x;
                         s2 = fmaf(x, x, s2);
-                        r[8 * u + e] = __float_as_uint(x);
+                    }
+                    tmem_ld_wait();
+                    if (c + 2 < 4) tmem_ld_32x32(t_acc + (c + 2) * 32, ra);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float x = __uint_as_float(rb[e]) + bias_s[half * 128 + (c + 1) * 32 + e];
+                        s1 += x;
+                        s2 = fmaf(x, x, s2);
                     }
                 }
-                tmem_st_32x32(t_acc + c * 32, r);
             }
-            tmem_st_wait();
             // exchange: the halves combine in shared memory, then 128 threads send the row's (sum, sum of squares) to every CTA
             loc_s[half][row] = make_float2(s1, s2);
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
@@ -233,8 +277,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float mean = S1 * inv_c;
             const double var_d = fmax((double)S2 * (double)inv_c - (double)mean * (double)mean, 0.0);
             const float rstd = rsqrtf((float)var_d + a.eps);
-            // pass 2: y = (x - mean) rstd gamma + beta -> bf16 rows over the residual in the staging tiles
+            // pass 2: y = (x - mean) rstd gamma + beta -> bf16 rows in the staging tiles (free once the previous tile's stores have read them)
             float mx = -INFINITY;
+            mbar_wait(&stg_free, tile_phase ^ 1);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t r[32];
@@ -242,6 +287,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* orow = smem + STG_OFF + (half * 2 + (c >> 1)) * TILE16 + row * 128;
                 const float* gg = gamma_s + half * 128 + c * 32;
                 const float* be = beta_s + half * 128 + c * 32;
+                const float* bb = bias_s + half * 128 + c * 32;
                 tmem_ld_wait();
                 if (c == 3) {                        // x is in registers: the MMAs of the tile after next may overwrite the accumulator
                     tc_fence_before();
@@ -253,7 +299,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float y[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        y[e] = (__uint_as_float(r[8 * u + e]) - mean) * rstd * gg[8 * u + e] + be[8 * u + e];
+                        y[e] = ((__uint_as_float(r[8 * u + e]) + bb[8 * u + e]) - mean) * rstd * gg[8 * u + e] + be[8 * u + e];
                         mx = fmaxf(mx, y[e]);
                     }
                     *reinterpret_cast<uint4*>(orow + ((((c & 1) * 4 + u) ^ sw) << 4)) =
@@ -274,14 +320,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tile_phase ^= 1;
         }
     } else {
-        // ---------------- residual loads and result stores through the four staging tiles ----------------
-        auto load_res = [&](int t) {
-            mbar_arrive_expect_tx(&res_full, 4 * TILE16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tma_load_2d(smem + STG_OFF + i * TILE16, &tmR, &res_full, col0 + i * 64, t * BM);
-        };
-        if (cl < row_tiles && elect_one()) load_res(cl);
-        __syncwarp();
+        // ---------------- result stores: four 64-column tiles per row tile ----------------
         uint32_t tile_phase = 0;
         for (int t = cl; t < row_tiles; t += ncl) {
             mbar_wait(&stg_full, tile_phase);
@@ -290,7 +329,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 4; ++i) tma_store_2d(&tmO, smem + STG_OFF + i * TILE16, col0 + i * 64, t * BM);
                 tma_store_commit();
                 tma_store_wait_read();
-                if (t + ncl < row_tiles) load_res(t + ncl);
+                mbar_arrive(&stg_free);
             }
             __syncwarp();
             tile_phase ^= 1;
