@@ -33,6 +33,8 @@ constexpr int RING_OFF = 0;
 // <STAGES, NPAIR> = <4, 2>: two staging pairs in flight and a 4-stage operand ring (3 stages starved the MMAs at K = 1280: 306 us
 // against 270).  <5, 1> was tried for the tensor-bound fc2 (K = 4 N): 188 us against 181 us for the generic kernel, and for the
 // ViT-H proj (K = N = 1280): 345 us against 267 us -- the staging pairs (bytes of residual in flight), not the ring, set the pace.
+// One loader / store warp per staging pair (so that a warp blocked in wait_group.read cannot delay the other pair) was slower too:
+// 101.5 against 93 us (ViT-B), 272 against 267 us (ViT-H).
 template <int STAGES, int NPAIR> __host__ __device__ constexpr int res_smem() { return STAGES * STAGE + NPAIR * PAIR + 1024; }
 constexpr int EPI_WARPS = 8;
 constexpr int STORE_WARP = 2 + EPI_WARPS;
