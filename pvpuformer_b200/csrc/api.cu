@@ -88,6 +88,16 @@ struct vpu_context {
     float click_table[32];
     int click_radius = 9;
     Profiler prof;
+    // small click batches (launch-latency-bound, replayed as CUDA graphs): independent parts of the forward -- the PPuE chain next
+    // to the ViT trunk, the image-side K|V|Q projection next to the prompt self-attention, the four pyramid levels -- are issued on
+    // side streams forked from / joined to the caller's stream with events, so a captured graph keeps them as parallel branches
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
+    ~vpu_context() {
+        for (auto& st : side) if (st) cudaStreamDestroy(st);
+        for (auto& e : ev_fork) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_join) if (e) cudaEventDestroy(e);
+    }
 
     int C() const { return d.embed_dim; }
     int grid() const { return d.img_size / d.patch; }
@@ -345,9 +355,27 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     const int heads = h.d.num_heads, hd = C / heads;
     typedef __nv_bfloat16 bf;
 
+    // side streams for small batches (vpu_context::side): fork = the side stream continues from the main stream's current position,
+    // join = the main stream waits for everything issued on the side stream so far
+    const cudaStream_t s_main = s;
+    static const bool branch_knob = [] { const char* e = vpu_debug_env("VPU_FWD_BRANCHES"); return !(e && e[0] == '0'); }();   // A/B knob, -DVPU_DEBUG builds
+    const bool branches = branch_knob && (size_t)B * h.N() <= 16384 && !h.prof.on && h.side[0] && !h.scalars.count("debug.stop_after_block");
+    auto on = [&](cudaStream_t t) { s = t; f.s = t; };
+    auto fork = [&](int k, int ev) -> int {
+        VPU_CHECK_CUDA(cudaEventRecord(h.ev_fork[ev], s_main));
+        VPU_CHECK_CUDA(cudaStreamWaitEvent(h.side[k], h.ev_fork[ev], 0));
+        return 0;
+    };
+    auto join = [&](int k) -> int {
+        VPU_CHECK_CUDA(cudaEventRecord(h.ev_join[k], h.side[k]));
+        VPU_CHECK_CUDA(cudaStreamWaitEvent(s_main, h.ev_join[k], 0));
+        return 0;
+    };
+
     // GroupNorm accumulators of the neck: cleared here so that no memset node sits between two kernels later on
     // (a non-kernel node would break the programmatic-dependent-launch chain, common.cuh)
     VPU_CHECK_CUDA(cudaMemsetAsync(f.buf<long long>("gn_sums"), 0, (size_t)8 * B * 2 * sizeof(long long), s));
+    if (branches) VPU_CHECK_CUDA(cudaEventRecord(h.ev_fork[0], s_main));      // the PPuE chain depends on nothing in this forward
     // ---- A1-A3, A7: fused image + coord-feature patch operand, one GEMM for both patch embeds ----
     CoordArgs ca;
     ca.image4 = image4; ca.points = pr.points; ca.extra_mask = pr.extra_mask; ca.n = pr.n; ca.H = img; ca.W = img;
@@ -420,7 +448,11 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         if (stop_after == i) return 0;
     }
 
-    // ---- A4-A6, A10: PPuE rows + FFN ----
+    // ---- A4-A6, A10: PPuE rows + FFN (small batches: a branch parallel to the ViT trunk) ----
+    if (branches) {
+        VPU_CHECK_CUDA(cudaStreamWaitEvent(h.side[0], h.ev_fork[0], 0));
+        on(h.side[0]);
+    }
     PpueArgs pa;
     RUN(fill_ppue_args(h, pr, pa));
     pa.out = f.buf<float>("ppue");
@@ -449,6 +481,10 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     float* rowmax = f.buf<float>("rowmax");
     f.stage = "dma";
     RUN(f.timed("cast", 0, 6.0 * MQ * C, [&] { return cast_add_launch(Q0, nullptr, Q0b, (size_t)MQ * C, s); }));
+    if (branches) {
+        on(s_main);
+        RUN(join(0));
+    }
     if (!fold || stop_after > 0)
         RUN(f.timed("cast", 0, 6.0 * M * C, [&] { return cast_add_launch(X, nullptr, X0b, (size_t)M * C, s); }));
     const int dh = h.d.dma_heads, Ci = C / 2, dself = C / dh, dcross = Ci / dh;
@@ -465,17 +501,28 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     for (int j = 0; j < h.d.dma_depth; ++j) {
         const std::string k = "dma" + std::to_string(j);
         const bool last = j + 1 == h.d.dma_depth;
+        // the image-side K|V (and step 4's Q) of this layer come from one GEMM whose positional term key_pe W^T is a precomputed
+        // additive table (transformer.py:444-449); it depends on the keys only: small batches run it beside steps (1) - (2a)
+        auto img_projection = [&]() -> int {
+            return f.gemm(Kin, C, k + ".img.w", M, 3 * Ci, C, nullptr, KVQ, true, 3 * Ci, ACT_NONE, nullptr, false, 0,
+                          f.Wf(k + ".img.tab"), N, nullptr, nullptr, TAB_PAD);
+        };
+        if (branches) {
+            RUN(fork(1, 1));
+            on(h.side[1]);
+            RUN(img_projection());
+            on(s_main);
+        }
         // (1) prompt self-attention (layer 0: output replaces the queries)
         RUN(f.attn(SQK, ldt, 0, SQK, ldt, C, SV, ldt, 0, f.buf<bf>("SO"), C, Q, Q, dh, dself, B, 1.0f / sqrtf((float)dself), false));
         RUN(f.gemm(f.buf<bf>("SO"), C, k + ".sa.o.w", MQ, C, C, f.Wf(k + ".sa.o.b"), T, false, C, ACT_NONE,
                    j == 0 ? nullptr : Qf, false, C));
         RUN(f.ln(T, k + ".n1", 1e-5f, MQ, Qt, Qb, Q0, QPb, nullptr, ldq));
         Qf = Qt;
-        // (2) tokens -> image cross attention; the image-side K|V (and step 4's Q) come from one GEMM whose
-        //     positional term key_pe W^T is a precomputed additive table (transformer.py:444-449)
+        // (2) tokens -> image cross attention
         RUN(f.gemm(QPb, ldq, k + ".t2i.q.w", MQ, Ci, C, f.Wf(k + ".t2i.q.b"), f.buf<bf>("TQ"), true, Ci));
-        RUN(f.gemm(Kin, C, k + ".img.w", M, 3 * Ci, C, nullptr, KVQ, true, 3 * Ci, ACT_NONE, nullptr, false, 0,
-                   f.Wf(k + ".img.tab"), N, nullptr, nullptr, TAB_PAD));
+        if (branches) RUN(join(1));
+        else RUN(img_projection());
         RUN(f.attn(f.buf<bf>("TQ"), Ci, 0, KVQ, 3 * Ci, 0, KVQ, 3 * Ci, Ci, f.buf<bf>("TO"), Ci, Q, N, dh, dcross, B,
                    1.0f / sqrtf((float)dcross), false));
         RUN(f.gemm(f.buf<bf>("TO"), Ci, k + ".t2i.o.w", MQ, C, Ci, f.Wf(k + ".t2i.o.b"), T, false, C, ACT_NONE, Qf, false, C));
@@ -534,6 +581,14 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     RUN(f.timed("merge", 0, 10.0 * M * C, [&] { return merge_launch(ma, s); }));
 
     // ---- A15: 4-scale pyramid (NHWC bf16; ConvT/Conv with stride == kernel are plain GEMMs) ----
+    // small batches: the four levels (neck chain + head conv pair) are independent until the head tail: one stream each
+    cudaStream_t lvl[4] = {s_main, s_main, s_main, s_main};
+    if (branches) {
+        for (int i = 0; i < 3; ++i) {
+            RUN(fork(i, 2));
+            lvl[i + 1] = h.side[i];
+        }
+    }
     f.stage = "neck";
     const int d4 = h.d4(), d8 = h.d8(), d32 = h.d32();
     const int* od = h.d.out_dims;
@@ -545,6 +600,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     auto S = [&](int i) { return sums + (size_t)i * B * 2; };
     typedef Fwd::Gn Gn;
     Gn gn;
+    on(lvl[0]);
     gn = Gn(); gn.out = S(0); gn.rows = N;
     RUN(f.gemm_ps(X0b, "d4.a.w", f.Wf("d4.a.b"), M, d4, C, g, f.buf<bf>("D4a"), &gn));
     RUN(f.gn(f.buf<bf>("D4a"), g2 * g2 * d4, d4, "d4.gn1", 1, S(0)));
@@ -555,6 +611,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
                ACT_NONE, nullptr, false, 0, nullptr, 0, &gn));
     RUN(f.gn(f.buf<bf>("P4"), g4 * g4 * od[0], od[0], "d4.gn3", 1, S(2)));
 
+    on(lvl[1]);
     gn = Gn(); gn.out = S(3); gn.rows = N;
     RUN(f.gemm_ps(f.buf<bf>("x2"), "d8.a.w", f.Wf("d8.a.b"), M, d8, C, g, f.buf<bf>("D8a"), &gn));
     gn = Gn(); gn.in = S(3); gn.in_count = (double)(g2 * g2) * d8; gn.wg = f.Wf("d8.b.wg"); gn.out = S(4); gn.rows = (int)(g2 * g2);
@@ -562,11 +619,13 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
                ACT_NONE, nullptr, false, 0, nullptr, 0, &gn));
     RUN(f.gn(f.buf<bf>("P8"), g2 * g2 * od[1], od[1], "d8.gn2", 1, S(4)));
 
+    on(lvl[2]);
     gn = Gn(); gn.out = S(5); gn.rows = N;
     RUN(f.gemm(f.buf<bf>("x3"), C, "d16.a.w", M, od[2], C, f.Wf("d16.a.b"), f.buf<bf>("P16"), true, od[2], ACT_NONE, nullptr, false, 0,
                nullptr, 0, &gn));
     RUN(f.gn(f.buf<bf>("P16"), (size_t)N * od[2], od[2], "d16.gn1", 1, S(5)));
 
+    on(lvl[3]);
     gn = Gn(); gn.out = S(6); gn.rows = (int)(gh * gh);
     RUN(f.gemm(f.buf<bf>("x4"), 4 * C, "d32.a.w", (int)(B * gh * gh), d32, 4 * C, f.Wf("d32.a.b"), f.buf<bf>("D32a"), true, d32,
                ACT_NONE, nullptr, false, 0, nullptr, 0, &gn));
@@ -584,6 +643,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     for (int i = 0; i < 4; ++i) {
         const std::string si = std::to_string(i);
         const int rows = (int)(B * res[i] * res[i]);
+        on(lvl[i]);
         GemmB2B bb;
         bb.A = f.buf<bf>(pyr[i]); bb.W1 = f.Wb("hd.c" + si + ".w"); bb.W2 = f.Wb("hd.f" + si + ".w"); bb.bias1 = f.Wf("hd.c" + si + ".b");
         bb.out = f.buf<bf>(("Y" + si).c_str()); bb.M = rows; bb.K1 = od[i]; bb.lda = od[i]; bb.ldo = hc;
@@ -603,6 +663,9 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
         hca.y[i] = f.buf<bf>(("Y" + si).c_str());
         hca.res[i] = (int)res[i];
     }
+    on(s_main);
+    if (branches)
+        for (int i = 0; i < 3; ++i) RUN(join(i));
     HeadTailArgs ht;
     for (int i = 0; i < 4; ++i) { ht.y[i] = hca.y[i]; ht.res[i] = hca.res[i]; }
     ht.B = B; ht.channels = hc; ht.bias = f.Wf("hd.f.b"); ht.wseg = f.Wf("hd.seg.w"); ht.seg_bias = h.scalars.at("hd.seg.b");
@@ -835,6 +898,9 @@ int vpu_finalize(vpu_handle h) {
     }
     VPU_REQUIRE(h->scalars.count("hd.seg.b"), "scalar 'hd.seg.b' is not set");
     if (int rc = gemm_init()) return rc;
+    for (auto& st : h->side) if (!st) VPU_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : h->ev_fork) if (!e) VPU_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : h->ev_join) if (!e) VPU_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (h->d.head_channels == 256 && (4 * h->grid()) % 16 == 0)       // interpolation-matrix table of the fused head tail
         if (int rc = head_tail_prepare(4 * h->grid())) return rc;
     h->finalized = true;
