@@ -73,6 +73,25 @@ def test_module_surface_and_packing_shapes(arch):
         assert packed["pe.tab"].shape == (N, C)
         assert packed["ffn.w1"].shape == (2048, 904) and not packed["ffn.w1"][:, 899:].any()
         assert packed["dma0.img.w"].shape == (3 * C // 2, C) and packed["dma0.img.tab"].shape == (N + 128, 3 * C // 2)
+        # merged token projections (packing.py): one GEMM over [tokens + PE | tokens] must reproduce the reference's separate
+        # q / k / v projections of transformer.py:436-461 (block rows [W 0] / [0 W])
+        assert packed["dma0.sa.qkv.w"].shape == (3 * C, C)
+        assert packed["dma0.tok.w"].shape == (4 * C, 2 * C) and packed["dma2.tok.w"].shape == (3 * C // 2, 2 * C)
+        assert torch.equal(packed["dma0.img.tab"][N:], packed["dma0.img.tab"][:128])          # periodic padding of the table
+        g = torch.Generator().manual_seed(5)
+        tok, pe = torch.randn(7, C, generator=g), torch.randn(7, C, generator=g)
+        both = torch.cat([tok + pe, tok], 1)
+        lin = lambda x, key: x @ sd[key + ".weight"].t() + sd[key + ".bias"]
+        l0, l1 = "neck.att.layers.0.", "neck.att.layers.1."
+        ref = torch.cat([lin(tok + pe, l0 + "cross_attn_image_to_token.k_proj"), lin(tok, l0 + "cross_attn_image_to_token.v_proj"),
+                         lin(tok + pe, l1 + "self_attn.q_proj"), lin(tok + pe, l1 + "self_attn.k_proj"), lin(tok, l1 + "self_attn.v_proj")], 1)
+        got = both @ packed["dma0.tok.w"].float().t() + packed["dma0.tok.b"]
+        assert (got - ref).abs().max().item() < 2e-2 * ref.abs().max().item()                # bf16 weights
+        l2 = "neck.att.layers.2."
+        ref = torch.cat([lin(tok + pe, l2 + "cross_attn_image_to_token.k_proj"), lin(tok, l2 + "cross_attn_image_to_token.v_proj"),
+                         lin(tok + pe, "neck.att.final_attn_token_to_image.q_proj")], 1)
+        got = both @ packed["dma2.tok.w"].float().t() + packed["dma2.tok.b"]
+        assert (got - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
         assert packed["d4.a.w"].shape == (4 * cfg.down_4_chan, C)
         assert packed["d32.a.w"].shape == (cfg.down_32_chan, 4 * C)
         assert "hd.seg.b" in scalars
