@@ -147,6 +147,19 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ partial, int chunk
         mean_rstd[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
     }
 }
+// same fit of the erf form as gelu_fast (common.cuh), evaluated through ONE MUFU (tanh.approx, relative error 2^-11, i.e. a quarter
+// of the half-ulp of the bf16 this kernel stores) instead of ex2 + rcp: the apply pass is bound by its instruction stream, not by HBM
+// (without the GELU it runs at 4.95 TB/s, with the two-MUFU form at 3.5, with this one at 3.7: 330 -> 291 us over the five passes)
+__device__ __forceinline__ float gelu_tanh1(float x) {
+    const float x2 = fminf(x * x, 64.0f);
+    float t = fmaf(-3.515167e-4f, x2, 3.700565e-2f);
+    t = fmaf(t, x2, 7.975079e-1f);
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * t));
+    const float h = 0.5f * x;
+    return fmaf(h, th, h);
+}
+
 // apply: every thread owns one channel octet (gamma / beta live in registers) and strides over pixels
 __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ x, size_t per_sample, int C,
                                                        const float2* __restrict__ mean_rstd, const long long* __restrict__ sums,
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float y = fmaf(f[k], sc[k], sh[k]);
-            f[k] = gelu ? gelu_fast(y) : y;
+            f[k] = gelu ? gelu_tanh1(y) : y;
         }
         return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     };
