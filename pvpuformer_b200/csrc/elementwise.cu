@@ -202,15 +202,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
         }
         return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     };
-    // four pixels per iteration: the four 16-byte loads are in flight together (one load per iteration left the kernel
-    // latency-bound at 2.4 TB/s)
+    // four pixels per iteration, and the loads of the next four are issued before the current four are evaluated and stored: without
+    // that a block's warps load, evaluate (MUFU) and store in lockstep and the MUFU time adds to the memory time instead of hiding
+    // under it
     size_t pix = (size_t)blockIdx.x * rows_per_block + prow;
-    for (; pix + 3 * step < npix; pix += 4 * step) {
-        uint4 v[4];
+    uint4 v[4], nv[4];
+    bool have = pix + 3 * step < npix;
+    if (have) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = p[(pix + u * step) * C8 + co];
+    }
+    while (have) {
+        const size_t npx = pix + 4 * step;
+        const bool next = npx + 3 * step < npix;
+        if (next) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nv[u] = p[(npx + u * step) * C8 + co];
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) p[(pix + u * step) * C8 + co] = apply(v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = nv[u];
+        pix = npx;
+        have = next;
     }
     for (; pix < npix; pix += step) p[pix * C8 + co] = apply(p[pix * C8 + co]);
 }
@@ -227,7 +241,11 @@ int groupnorm_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, const fl
     while (C8 / zsplit > 256 || C8 % zsplit) ++zsplit;
     const int C8z = C8 / zsplit, threads = C8z * (256 / C8z);
     const size_t npix = per_sample / C;
-    int blocks = (int)((npix + 4 * (threads / C8z) - 1) / (4 * (threads / C8z)));     // four pixels per thread
+    // 16 pixels per thread (four pipelined iterations; 4 / 8 / 16 / 32 measured 306 / 263 / 249 / 255 us over the neck's five passes at
+    // batch 64) unless that leaves SMs without a block (small batches): then 4
+    const int rpb = threads / C8z;
+    int blocks = (int)((npix + 16 * rpb - 1) / (16 * rpb));
+    if ((long long)blocks * B * zsplit < 4 * 148) blocks = (int)((npix + 4 * rpb - 1) / (4 * rpb));
     if (blocks > 148 * 8) blocks = 148 * 8;
     VPU_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks, B, zsplit), dim3(threads), 0, stream, x, per_sample, C, mean_rstd, nullptr, gamma, beta, gelu));
     VPU_CHECK_CUDA(cudaGetLastError());
@@ -244,7 +262,11 @@ int groupnorm_apply_launch(__nv_bfloat16* x, int B, size_t per_sample, int C, co
     while (C8 / zsplit > 256 || C8 % zsplit) ++zsplit;
     const int C8z = C8 / zsplit, threads = C8z * (256 / C8z);
     const size_t npix = per_sample / C;
-    int blocks = (int)((npix + 4 * (threads / C8z) - 1) / (4 * (threads / C8z)));     // four pixels per thread
+    // 16 pixels per thread (four pipelined iterations; 4 / 8 / 16 / 32 measured 306 / 263 / 249 / 255 us over the neck's five passes at
+    // batch 64) unless that leaves SMs without a block (small batches): then 4
+    const int rpb = threads / C8z;
+    int blocks = (int)((npix + 16 * rpb - 1) / (16 * rpb));
+    if ((long long)blocks * B * zsplit < 4 * 148) blocks = (int)((npix + 4 * rpb - 1) / (4 * rpb));
     if (blocks > 148 * 8) blocks = 148 * 8;
     VPU_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks, B, zsplit), dim3(threads), 0, stream, x, per_sample, C, nullptr, sums, gamma, beta, gelu));
     VPU_CHECK_CUDA(cudaGetLastError());
