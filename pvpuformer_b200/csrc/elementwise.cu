@@ -536,10 +536,13 @@ __global__ void __launch_bounds__(256) upsample_ac4_kernel(const float* __restri
     const int W4 = W / 4, H4 = H / 4;
     const size_t total = planes * H4 * W4;
     const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
-    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int x4 = (int)(idx % W4);
-        const int Y = (int)((idx / W4) % H4);
-        const size_t pl = idx / ((size_t)W4 * H4);
+    // 32-bit index arithmetic (total < 2^31 is checked by the launcher): three 64-bit divisions per 4 x 4 block were a third of the
+    // kernel's instructions
+    const unsigned total32 = (unsigned)total, stride = gridDim.x * blockDim.x, per_plane = (unsigned)(W4 * H4);
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += stride) {
+        const unsigned plu = idx / per_plane, rem = idx - plu * per_plane;
+        const int Y = (int)(rem / (unsigned)W4), x4 = (int)(rem - (unsigned)Y * (unsigned)W4);
+        const size_t pl = plu;
         int xo[4], yo[4];
         float lx[4], ly[4];
 #pragma unroll
@@ -575,14 +578,15 @@ __global__ void __launch_bounds__(256) upsample_ac4_kernel(const float* __restri
                 const float a = s1 ? hz[1][k] : hz[0][k], b = s1 ? hz[2][k] : hz[1][k];
                 v[k] = (1.f - ly[yy]) * a + ly[yy] * b;
             }
-            *reinterpret_cast<float4*>(o + (size_t)yy * W) = make_float4(v[0], v[1], v[2], v[3]);
+            __stcs(reinterpret_cast<float4*>(o + (size_t)yy * W), make_float4(v[0], v[1], v[2], v[3]));     // written once, read by the host
         }
     }
 }
 
 int upsample_ac_launch(const float* in, float* out, int h, int w, int H, int W, size_t planes, cudaStream_t stream) {
     VPU_REQUIRE(W % 4 == 0, "upsample: output width must be a multiple of 4");
-    if (H % 4 == 0 && H > 1 && W > 1 && 3 * (h - 1) < (H - 1) && 3 * (w - 1) < (W - 1)) {   // 4 outputs within one source step
+    if (H % 4 == 0 && H > 1 && W > 1 && 3 * (h - 1) < (H - 1) && 3 * (w - 1) < (W - 1) &&
+        planes * (H / 4) * (W / 4) < (size_t)1 << 31) {   // 4 outputs within one source step
         const size_t total = planes * (H / 4) * (W / 4);
         size_t grid = (total + 255) / 256;
         if (grid > 148 * 32) grid = 148 * 32;
