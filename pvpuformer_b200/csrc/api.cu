@@ -105,6 +105,10 @@ struct vpu_context {
     int Q() const { return 2 * d.num_max_points; }
     int K0() const { return 6 * d.patch * d.patch; }    // fused (image | coords) patch-embed K
     int K0s() const { return 10 * d.patch * d.patch; }  // + split-bf16 residual planes of image and prev mask
+    // row strides of the patch operand and of the two patch-embed weights: K rounded up to 64 elements, so that every row starts on a
+    // 128-byte line (patch 14: K = 1960 / 1176 left the rows 16-byte aligned only and the ViT-H patch-embed GEMMs at half rate)
+    int K0s_ld() const { return (K0s() + 63) / 64 * 64; }
+    int K0_ld() const { return (K0() + 63) / 64 * 64; }
     int ppue_dim() const { return 2 * d.img_size + 3; }
     int ppue_ld() const { return (ppue_dim() + 7) / 8 * 8; }
     int d4() const { return std::max(d.out_dims[0] * 2, d.embed_dim / 2); }
@@ -126,7 +130,7 @@ Plan make_plan(const vpu_context& h, int B) {
     const size_t g2 = 2 * g, g4 = 4 * g, gh = g / 2, hc = h.d.head_channels;
     p.add("ppue", (size_t)B * Q * h.ppue_dim() * 4);
     p.add("ppue_b", MQ * h.ppue_ld() * 2);
-    p.add("A0", M * h.K0s() * 2);
+    p.add("A0", M * h.K0s_ld() * 2);
     p.add("X", M * C * 4);
     p.add("Xn", M * C * 2);
     p.add("lnstats", M * (size_t)gemm_ln_slots_max((int)C) * sizeof(float2));
@@ -382,12 +386,12 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     ca.radius = h.d.norm_radius;
     f.stage = "patch_embed";
     RUN(f.timed("patch_operand", 0, (double)B * img * img * (16.0 + 20.0), [&] {
-        return patch_operand_launch(ca, B, f.buf<bf>("A0"), h.d.patch, h.K0s(), s);
+        return patch_operand_launch(ca, B, f.buf<bf>("A0"), h.d.patch, h.K0s_ld(), s);
     }));
     // 3-term split-bf16 product (A_hi + A_lo)(W_hi + W_lo) ~ A_hi W_hi + A_lo W_hi + A_hi W_lo: the token
     // embedding feeds the fp32 residual stream of every block, so it is computed to ~fp32 accuracy.
     float* X = f.buf<float>("X");
-    RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w", M, C, h.K0s(), nullptr, X, false, C, ACT_NONE, nullptr, false, 0,
+    RUN(f.gemm(f.buf<bf>("A0"), h.K0s_ld(), "pe.w", M, C, h.K0s(), nullptr, X, false, C, ACT_NONE, nullptr, false, 0,
                f.Wf("pe.tab"), N));
     const bool fold = h.ln_fold();
     typedef Fwd::Ln Ln;
@@ -396,10 +400,10 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
     Ln ln_out;                       // residual GEMMs: fp32 X + bf16 copy + row statistics for the LayerNorm that follows
     ln_out.out = lnst; ln_out.out_bf16 = f.buf<bf>("Xn"); ln_out.row = f.buf<float2>("lnrow");
     if (fold)
-        RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w_lo", M, C, h.K0(), f.Wf("pe.zero_b"), X, false, C, ACT_NONE, X, false, C, nullptr, 0,
+        RUN(f.gemm(f.buf<bf>("A0"), h.K0s_ld(), "pe.w_lo", M, C, h.K0(), f.Wf("pe.zero_b"), X, false, C, ACT_NONE, X, false, C, nullptr, 0,
                    nullptr, &ln_out));
     else
-        RUN(f.gemm(f.buf<bf>("A0"), h.K0s(), "pe.w_lo", M, C, h.K0(), nullptr, X, false, C, ACT_NONE, X, false, C));
+        RUN(f.gemm(f.buf<bf>("A0"), h.K0s_ld(), "pe.w_lo", M, C, h.K0(), nullptr, X, false, C, ACT_NONE, X, false, C));
 
     // ---- A8-A9: ViT blocks ----
     bf* Xn = f.buf<bf>("Xn");
@@ -730,8 +734,8 @@ std::vector<Need> needed_weights(const vpu_context& h) {
         v.push_back({k + ".g", VPU_F32, {c}});
         v.push_back({k + ".b", VPU_F32, {c}});
     };
-    v.push_back({"pe.w", VPU_BF16, {C, h.K0s()}});
-    v.push_back({"pe.w_lo", VPU_BF16, {C, h.K0()}});
+    v.push_back({"pe.w", VPU_BF16, {C, h.K0s_ld()}});        // zero columns past K (packing.py)
+    v.push_back({"pe.w_lo", VPU_BF16, {C, h.K0_ld()}});
     v.push_back({"pe.tab", VPU_F32, {N, C}});
     if (h.ln_fold()) v.push_back({"pe.zero_b", VPU_F32, {C}});
     for (int i = 0; i < h.d.depth; ++i) {

@@ -43,6 +43,12 @@ TAB_PAD = 128   # api.cu TAB_PAD: the positional tables of the image-side projec
                 # so that a 128-row TMA box starting at row (m mod N) never wraps (gemm_res.cu MODE_TAB)
 
 
+def _pad_cols(w, mult=64):
+    k = w.shape[1]
+    kp = (k + mult - 1) // mult * mult
+    return w if kp == k else torch.cat([w, w.new_zeros(w.shape[0], kp - k)], 1)
+
+
 def _pad_table(t):
     reps = (TAB_PAD + t.shape[0] - 1) // t.shape[0] + 1
     return torch.cat([t] * reps, 0)[: t.shape[0] + TAB_PAD].contiguous()
@@ -79,8 +85,9 @@ def pack_weights(sd, cfg, device):
     pp = p * p
     # split-bf16 (prompt.cu patch_operand_kernel): A = [hi planes (6pp) | lo planes of R,G,B,prev (4pp)];
     # GEMM 1: A x [W_hi | W_hi[:, :4pp]], GEMM 2: A[:, :6pp] x W_lo
-    W("pe.w", torch.cat([w_hi, w_hi[:, :4 * pp]], dim=1))
-    W("pe.w_lo", w_pe - w_hi.float())
+    # rows padded with zero columns to a multiple of 64 elements (api.cu K0s_ld / K0_ld): 128-byte aligned rows for the TMA loads
+    W("pe.w", _pad_cols(torch.cat([w_hi, w_hi[:, :4 * pp]], dim=1)))
+    W("pe.w_lo", _pad_cols(w_pe - w_hi.float()))
     fold = (w_img * (mean / std)).sum(dim=(1, 2, 3))             # [C]
     tab = f["backbone.pos_embed"][0, 1:] + (f["backbone.patch_embed.proj.bias"] + f["patch_embed_coords.proj.bias"] - fold)
     F32("pe.tab", tab)
