@@ -15,7 +15,9 @@
 // exact in the fp32 accumulator).  The producer warp therefore prefetches the residual with the operands, and the epilogue reads
 // nothing but TMEM; staging it in the output tiles exposed an HBM round trip per tile (84 us against 64 us for ViT-B, batch 64;
 // the unfused pair took 114 us).  What bounds it now (ncu, profiles/ncu_full_r2.md): the 3-stage operand ring -- a 1-CTA tile re-reads
-// its 192 KB weight slice per 128 rows, 352 KB of TMA loads per tile with 144 KB in flight; shared memory is full.
+// its 192 KB weight slice per 128 rows, 352 KB of TMA loads per tile with 144 KB in flight; shared memory is full.  (128 columns
+// per CTA -- clusters of 6 / 8, five 32 KB stages, half the weight bytes per CTA and tile -- measured slower: 67 against 63 us for
+// ViT-B, 120 against 105 us for ViT-L: the larger cluster's lockstep costs more than the deeper ring gains.)
 // Two accumulators: the MMAs of the next row tile run under the epilogue of the current one.
 #include "gemm.cuh"
 #include "tc_attn.cuh"
