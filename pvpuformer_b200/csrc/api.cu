@@ -248,11 +248,14 @@ struct Fwd {
         const float2* in = nullptr;    // the same buffer on the consuming side
         const float* s = nullptr;
         float eps = 1e-6f;
+        bool unused = false;           // producing side: nobody reads these statistics (the last block's fc2): no finaliser launch
     };
     // The row statistics of the LayerNorm fusion are finalised by ln_rowstats_kernel, a launch of its own after every residual GEMM.
     // Finalising them inside the producing GEMM (the last-arriving column tile of a 32-row block adds the slots, arrival counter
     // + __threadfence) was tried in round 2: +0.3 ms per batch-64 step in three A/B alternations (the fence makes every epilogue
-    // warp of proj / fc2 wait for its own 40 KB of tile stores) and no gain at batch 2; removed.
+    // warp of proj / fc2 wait for its own 40 KB of tile stores) and no gain at batch 2; removed.  Finalising them in the CONSUMER's
+    // epilogue for small problems (each lane one row from the raw slots, results exchanged by shuffles; same arithmetic, same bits)
+    // was slower too: batch 2 1.297 -> 1.318 ms, batch 8 2.465 -> 2.684 ms.
     // out = act(A W^T + bias [+ tab] [+ res])
     int gemm(const __nv_bfloat16* A, int lda, const std::string& wkey, int M, int Nn, int K, const float* bias, void* out,
              bool out_bf16, int ldo, int act = ACT_NONE, const void* res = nullptr, bool res_bf16 = false, int ldr = 0,
@@ -274,7 +277,7 @@ struct Fwd {
         const int grc = timed("gemm", 2.0 * M * Nn * K, by, [&] { return gemm_launch(p, s, h.gemm_impl); });
         label.clear();
         if (grc) return grc;
-        if (ln && ln->out)      // finalise the row statistics for the LayerNorm-folded GEMM that follows
+        if (ln && ln->out && !ln->unused)      // finalise the row statistics for the LayerNorm-folded GEMM that follows
             return timed("lnstats", 0, (double)M * (p.epi.ln_slots + 1) * 8.0,
                          [&] { return ln_rowstats_launch(ln->out, M, p.epi.ln_slots, h.C(), ln->eps, ln->row, s); });
         return 0;
@@ -441,7 +444,7 @@ int run_forward(vpu_context& h, const float* image4, const vpu_prompts& pr, int 
                        nullptr, &ln_in));
             // the last block's bf16 copy is the DMA stage's key operand
             Ln lo = ln_out;
-            if (i == h.d.depth) lo.out_bf16 = X0b;
+            if (i == h.d.depth) { lo.out_bf16 = X0b; lo.unused = true; }
             RUN(f.gemm(Hh, 4 * C, k + ".fc2.w", M, C, 4 * C, f.Wf(k + ".fc2.b"), X, false, C, ACT_NONE, X, false, C, nullptr, 0, nullptr, &lo));
         } else {
             RUN(f.gemm(AO, C, k + ".proj.w", M, C, C, f.Wf(k + ".proj.b"), X, false, C, ACT_NONE, X, false, C));
